@@ -1,0 +1,136 @@
+/* nzcb.h -- C ABI of libnzcb.so, the B200-native replacement for the proving /
+ * witness path that noway/nzcb-circom reaches through third-party JS:
+ *
+ *   snarkjs 0.4.12 plonk.prove / fullProve / setup      (/root/reference/yarn.lock:7279,
+ *                                                        recipe at /root/reference/Makefile:54-62)
+ *   ffjavascript 0.2.48 G1.multiExpAffine, Fr.fft/ifft  (/root/reference/yarn.lock:3905)
+ *   circom_tester.wasm(...).calculateWitness(input, sanityCheck)
+ *                                                       (/root/reference/test/nzcp.js:3,42;
+ *                                                        test/cbor.js, test/quinSelector.js call sites)
+ *
+ * Conventions
+ *   - every function returns an int32 status: 0 = OK, < 0 = NZCB_E_*; nothing
+ *     throws or aborts across the ABI; nzcb_last_error(ctx) returns a UTF-8
+ *     message for the last failure on that ctx (snarkjs' own strings where it
+ *     has one: "Invalid witness length", "Copy constraints does not match",
+ *     "T Polynomial is not divisible", "Polinomial does not divide").
+ *   - plain pointers and sizes only.  All *input* buffers are HOST memory,
+ *     borrowed for the duration of the call; all *output* buffers are caller-
+ *     allocated HOST memory.  Device-resident variants end in _dev.
+ *   - byte layouts are exactly the iden3 file layouts so JS
+ *     {type:"mem"} buffers pass straight through:
+ *       "LEM" = 32-byte little-endian Montgomery (R = 2^256) field element,
+ *       "LE"  = 32-byte little-endian canonical,  "BE" = big-endian canonical;
+ *       G1 affine = x||y (64 B), infinity = all zero.
+ *   - one ctx = one GPU = one CUDA stream set; a ctx is thread-compatible
+ *     (one host thread at a time).  One process per GPU is the intended use.
+ *   - there is no CPU fallback: every entry point fails with NZCB_E_CUDA if no
+ *     sm_100-class device is usable.
+ */
+#ifndef NZCB_H
+#define NZCB_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NZCB_OK 0
+#define NZCB_E_INVALID (-1)   /* bad argument / malformed file */
+#define NZCB_E_CUDA (-2)      /* CUDA runtime failure (message has the detail) */
+#define NZCB_E_WITNESS (-3)   /* "Invalid witness length" and friends */
+#define NZCB_E_COPY (-4)      /* "Copy constraints does not match" */
+#define NZCB_E_DIVIDE (-5)    /* "T Polynomial is not divisible" / "Polinomial does not divide" */
+#define NZCB_E_ASSERT (-6)    /* witness program: "Assert Failed" (circom_runtime error 4) */
+#define NZCB_E_NOMEM (-7)
+
+typedef struct nzcb_ctx nzcb_ctx;
+typedef struct nzcb_zkey nzcb_zkey;
+typedef struct nzcb_circuit nzcb_circuit;
+
+/* proof = what snarkjs puts in proof.json, binary:
+ * nine G1 points as x||y BE canonical (toRprUncompressed) and seven Fr BE. */
+typedef struct nzcb_proof {
+    uint8_t A[64], B[64], C[64], Z[64], T1[64], T2[64], T3[64], Wxi[64], Wxiw[64];
+    uint8_t eval_a[32], eval_b[32], eval_c[32], eval_s1[32], eval_s2[32], eval_zw[32], eval_r[32];
+} nzcb_proof;
+
+/* ---- context ---------------------------------------------------------- */
+int32_t nzcb_ctx_create(int32_t device_id, nzcb_ctx** out);
+void nzcb_ctx_free(nzcb_ctx* ctx);
+const char* nzcb_last_error(const nzcb_ctx* ctx);
+/* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
+uint64_t nzcb_launch_count(const nzcb_ctx* ctx);
+/* milliseconds of device time of the last timed entry point (CUDA events on the ctx stream) */
+float nzcb_last_device_ms(const nzcb_ctx* ctx);
+
+/* integer-pipe microbenchmark (roofline denominators): kind 0 = IMAD,
+ * 1 = IMAD.WIDE.U32, 2 = Fr Montgomery multiply, 3 = Fq multiply, 4 = IMAD.HI.U32,
+ * 5 = Fr multiply, portable CIOS variant; result in ops/s */
+int32_t nzcb_microbench(nzcb_ctx* ctx, int32_t kind, uint32_t iters, uint32_t blocks_per_sm, double* ops_per_s);
+/* device self-test: carry-chain multiply vs portable CIOS on n random operand pairs x 16 */
+int32_t nzcb_selftest_mul(nzcb_ctx* ctx, uint32_t n, uint64_t* mismatches);
+
+/* ---- primitives: ffjavascript Fr.fft / Fr.ifft / G1.multiExpAffine ------ */
+/* In-place NTT of 2^log_n LEM elements, natural order in and out; inverse
+ * includes the 1/N factor. */
+int32_t nzcb_ntt_fr(nzcb_ctx* ctx, uint8_t* data_lem, uint32_t log_n, int32_t inverse);
+/* sum_i scalars[i] * bases[i];  bases n x 64 B affine LEM, scalars n x 32 B LE
+ * canonical (what multiExpAffine takes after fromMontgomery); result affine LEM. */
+int32_t nzcb_msm_g1(nzcb_ctx* ctx, const uint8_t* bases_affine_lem, const uint8_t* scalars_le, size_t n,
+                    uint8_t out_affine_lem[64]);
+/* device-resident primitives for the roofline measurement (buffers from nzcb_dev_alloc) */
+int32_t nzcb_dev_alloc(nzcb_ctx* ctx, size_t bytes, void** dptr);
+int32_t nzcb_dev_free(nzcb_ctx* ctx, void* dptr);
+int32_t nzcb_dev_upload(nzcb_ctx* ctx, void* dptr, const void* host, size_t bytes);
+int32_t nzcb_dev_download(nzcb_ctx* ctx, void* host, const void* dptr, size_t bytes);
+int32_t nzcb_ntt_fr_dev(nzcb_ctx* ctx, void* d_data_lem, uint32_t log_n, int32_t inverse);
+int32_t nzcb_msm_g1_dev(nzcb_ctx* ctx, const void* d_bases_affine_lem, const void* d_scalars_le, size_t n,
+                        uint8_t out_affine_lem[64]);
+
+/* ---- SRS + setup: `snarkjs powersoftau new` / `plonk setup` roles --------- */
+/* [tau^i]G1, i < count, affine LEM (insecure known-trapdoor SRS, Makefile:64-67 role) */
+int32_t nzcb_srs_g1(nzcb_ctx* ctx, const uint8_t tau_le[32], size_t count, uint8_t* out_affine_lem);
+/* snarkjs `plonk setup`: r1cs file bytes + SRS -> PLONK zkey v1
+ * bytes.  Call with zkey_out = NULL to get the size in *zkey_len. */
+int32_t nzcb_plonk_setup(nzcb_ctx* ctx, const uint8_t* r1cs, size_t r1cs_len, const uint8_t* srs_g1_lem,
+                         size_t srs_count, const uint8_t x2_g2_lem[128], uint8_t* zkey_out, size_t* zkey_len);
+
+/* ---- prover: snarkjs plonk.prove(zkey, wtns) ---------------------------- */
+/* parse a PLONK zkey (v1, 14 sections) and make it device resident once */
+int32_t nzcb_zkey_load(nzcb_ctx* ctx, const uint8_t* zkey, size_t len, nzcb_zkey** out);
+void nzcb_zkey_free(nzcb_zkey* zk);
+int32_t nzcb_zkey_info(const nzcb_zkey* zk, uint32_t* n_vars, uint32_t* n_public, uint32_t* domain_size,
+                       uint32_t* n_additions, uint32_t* n_constraints);
+/* blinders: b1..b9 as 9 x 32 B LE canonical (what Fr.random() would have
+ * returned, in call order); NULL -> drawn from the OS CSPRNG.
+ * public_le: nPublic x 32 B LE canonical (publicSignals). */
+int32_t nzcb_plonk_prove(nzcb_ctx* ctx, const nzcb_zkey* zk, const uint8_t* wtns, size_t wtns_len,
+                         const uint8_t* blinders_le, nzcb_proof* out, uint8_t* public_le);
+/* B independent proofs on this ctx's GPU (multi-GPU = one ctx/process per GPU,
+ * proofs sharded by the caller; no collective).  wtns[i] / wtns_len[i] per proof. */
+int32_t nzcb_plonk_prove_batch(nzcb_ctx* ctx, const nzcb_zkey* zk, const uint8_t* const* wtns,
+                               const size_t* wtns_len, const uint8_t* blinders_le /* B x 9 x 32 or NULL */,
+                               size_t B, nzcb_proof* out, uint8_t* public_le /* B x nPublic x 32 */,
+                               int32_t* status /* B */);
+/* proof.json / public.json text exactly as snarkjs prints them (key order of A.2 step 6) */
+int32_t nzcb_proof_to_json(const nzcb_proof* proof, char* buf, size_t* len);
+
+/* ---- witness: circom_tester calculateWitness / snarkjs wtns.calculate ---- */
+/* load a compiled witness program (nzcb .wprog bytes emitted by the circuit builder) */
+int32_t nzcb_circuit_load(nzcb_ctx* ctx, const uint8_t* wprog, size_t len, nzcb_circuit** out);
+void nzcb_circuit_free(nzcb_circuit* c);
+int32_t nzcb_circuit_info(const nzcb_circuit* c, uint32_t* n_witness, uint32_t* n_inputs, uint32_t* n_outputs);
+/* B passes: inputs_le is B x nInputs x 32 B LE canonical, in main-input
+ * declaration order (the order circom puts them in the witness);
+ * wtns_out (may be NULL) receives B x nWitness x 32 B LE canonical -- the
+ * payload of .wtns section 2; status[i] = 0 or NZCB_E_ASSERT per pass (a failed
+ * pass never fails the batch, test/quinSelector.js:66 semantics). */
+int32_t nzcb_witness_batch(nzcb_ctx* ctx, const nzcb_circuit* c, const uint8_t* inputs_le, size_t B,
+                           uint8_t* wtns_out, int32_t* status);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NZCB_H */

@@ -1,0 +1,160 @@
+"""ctypes binding of libnzcb.so (include/nzcb.h).  Fails loudly when the CUDA
+library is missing or no B200 is usable -- there is no CPU fallback."""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libnzcb.so")
+
+NZCB_OK = 0
+NZCB_E_INVALID = -1
+NZCB_E_CUDA = -2
+NZCB_E_WITNESS = -3
+NZCB_E_COPY = -4
+NZCB_E_DIVIDE = -5
+NZCB_E_ASSERT = -6
+NZCB_E_NOMEM = -7
+
+
+class NzcbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"nzcb error {code}: {msg}")
+        self.code = code
+        self.message = msg
+
+
+class Proof(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_uint8 * 64) for n in ("A", "B", "C", "Z", "T1", "T2", "T3", "Wxi", "Wxiw")] + [
+        (n, ctypes.c_uint8 * 32) for n in ("eval_a", "eval_b", "eval_c", "eval_s1", "eval_s2", "eval_zw", "eval_r")
+    ]
+
+
+_lib = None
+
+_vp = ctypes.c_void_p
+_cp = ctypes.c_char_p
+_sz = ctypes.c_size_t
+_i32 = ctypes.c_int32
+_u32 = ctypes.c_uint32
+
+# name -> (restype, argtypes); every symbol include/nzcb.h declares
+SIGNATURES = {
+    "nzcb_ctx_create": (_i32, [_i32, ctypes.POINTER(_vp)]),
+    "nzcb_ctx_free": (None, [_vp]),
+    "nzcb_last_error": (_cp, [_vp]),
+    "nzcb_launch_count": (ctypes.c_uint64, [_vp]),
+    "nzcb_last_device_ms": (ctypes.c_float, [_vp]),
+    "nzcb_microbench": (_i32, [_vp, _i32, _u32, _u32, ctypes.POINTER(ctypes.c_double)]),
+    "nzcb_selftest_mul": (_i32, [_vp, _u32, ctypes.POINTER(ctypes.c_uint64)]),
+    "nzcb_ntt_fr": (_i32, [_vp, _vp, _u32, _i32]),
+    "nzcb_msm_g1": (_i32, [_vp, _vp, _vp, _sz, _vp]),
+    "nzcb_dev_alloc": (_i32, [_vp, _sz, ctypes.POINTER(_vp)]),
+    "nzcb_dev_free": (_i32, [_vp, _vp]),
+    "nzcb_dev_upload": (_i32, [_vp, _vp, _vp, _sz]),
+    "nzcb_dev_download": (_i32, [_vp, _vp, _vp, _sz]),
+    "nzcb_ntt_fr_dev": (_i32, [_vp, _vp, _u32, _i32]),
+    "nzcb_msm_g1_dev": (_i32, [_vp, _vp, _vp, _sz, _vp]),
+    "nzcb_srs_g1": (_i32, [_vp, _vp, _sz, _vp]),
+    "nzcb_plonk_setup": (_i32, [_vp, _vp, _sz, _vp, _sz, _vp, _vp, ctypes.POINTER(_sz)]),
+    "nzcb_zkey_load": (_i32, [_vp, _vp, _sz, ctypes.POINTER(_vp)]),
+    "nzcb_zkey_free": (None, [_vp]),
+    "nzcb_zkey_info": (_i32, [_vp] + [ctypes.POINTER(_u32)] * 5),
+    "nzcb_plonk_prove": (_i32, [_vp, _vp, _vp, _sz, _vp, ctypes.POINTER(Proof), _vp]),
+    "nzcb_plonk_prove_batch": (_i32, [_vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp]),
+    "nzcb_proof_to_json": (_i32, [ctypes.POINTER(Proof), _vp, ctypes.POINTER(_sz)]),
+    "nzcb_circuit_load": (_i32, [_vp, _vp, _sz, ctypes.POINTER(_vp)]),
+    "nzcb_circuit_free": (None, [_vp]),
+    "nzcb_circuit_info": (_i32, [_vp] + [ctypes.POINTER(_u32)] * 3),
+    "nzcb_witness_batch": (_i32, [_vp, _vp, _vp, _sz, _vp, _vp]),
+}
+
+
+def load():
+    """dlopen libnzcb.so and bind every declared symbol (no GPU needed for this)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NzcbError(NZCB_E_CUDA, f"{LIB_PATH} is missing: run `python __graft_entry__.py build` "
+                                     "(nvcc, sm_100a).  There is no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError = header/library mismatch: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+class Context:
+    """One GPU, one stream set (nzcb_ctx)."""
+
+    def __init__(self, device_id=0):
+        self.lib = load()
+        h = _vp()
+        rc = self.lib.nzcb_ctx_create(device_id, ctypes.byref(h))
+        if rc != 0:
+            raise NzcbError(rc, self.lib.nzcb_last_error(None).decode())
+        self.h = h
+
+    def check(self, rc):
+        if rc != 0:
+            raise NzcbError(rc, self.lib.nzcb_last_error(self.h).decode())
+
+    @property
+    def launches(self):
+        return int(self.lib.nzcb_launch_count(self.h))
+
+    @property
+    def last_device_ms(self):
+        return float(self.lib.nzcb_last_device_ms(self.h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.nzcb_ctx_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def microbench(self, kind, iters=2000, blocks_per_sm=8):
+        v = ctypes.c_double()
+        self.check(self.lib.nzcb_microbench(self.h, kind, iters, blocks_per_sm, ctypes.byref(v)))
+        return v.value
+
+    def selftest_mul(self, n=1 << 20):
+        v = ctypes.c_uint64()
+        self.check(self.lib.nzcb_selftest_mul(self.h, n, ctypes.byref(v)))
+        return v.value
+
+    # --- device buffers (bench / roofline path) ---
+    def dev_alloc(self, nbytes):
+        p = _vp()
+        self.check(self.lib.nzcb_dev_alloc(self.h, nbytes, ctypes.byref(p)))
+        return p
+
+    def dev_free(self, p):
+        self.check(self.lib.nzcb_dev_free(self.h, p))
+
+    def dev_upload(self, p, data):
+        buf = (ctypes.c_uint8 * len(data)).from_buffer_copy(data) if not isinstance(data, ctypes.Array) else data
+        self.check(self.lib.nzcb_dev_upload(self.h, p, buf, len(data)))
+
+    def dev_download(self, p, nbytes):
+        buf = (ctypes.c_uint8 * nbytes)()
+        self.check(self.lib.nzcb_dev_download(self.h, buf, p, nbytes))
+        return bytes(buf)
+
+
+_default_ctx = {}
+
+
+def default_context(device_id=None):
+    if device_id is None:
+        device_id = int(os.environ.get("LOCAL_RANK", "0"))
+    if device_id not in _default_ctx:
+        _default_ctx[device_id] = Context(device_id)
+    return _default_ctx[device_id]

@@ -1,0 +1,92 @@
+// Context lifetime and small device-memory helpers of the C ABI (include/nzcb.h).
+#include "common.cuh"
+
+using namespace nzcb;
+
+static thread_local char g_noctx_err[256] = "nzcb: no context";
+
+extern "C" int32_t nzcb_ctx_create(int32_t device_id, nzcb_ctx** out) {
+    if (!out) return NZCB_E_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        snprintf(g_noctx_err, sizeof(g_noctx_err),
+                 "nzcb: no CUDA device available (%s); there is no CPU fallback",
+                 e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+        cudaGetLastError();
+        return NZCB_E_CUDA;
+    }
+    if (device_id < 0 || device_id >= ndev) {
+        snprintf(g_noctx_err, sizeof(g_noctx_err), "nzcb: device %d out of range (have %d)", device_id, ndev);
+        return NZCB_E_INVALID;
+    }
+    cudaDeviceProp prop;
+    if (cudaSetDevice(device_id) != cudaSuccess || cudaGetDeviceProperties(&prop, device_id) != cudaSuccess) {
+        snprintf(g_noctx_err, sizeof(g_noctx_err), "nzcb: cannot select device %d", device_id);
+        cudaGetLastError();
+        return NZCB_E_CUDA;
+    }
+    if (prop.major < 10) {
+        snprintf(g_noctx_err, sizeof(g_noctx_err), "nzcb: device %d is sm_%d%d; this library is built for sm_100a only",
+                 device_id, prop.major, prop.minor);
+        return NZCB_E_CUDA;
+    }
+    nzcb_ctx* ctx = new nzcb_ctx();
+    ctx->device = device_id;
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+        snprintf(g_noctx_err, sizeof(g_noctx_err), "nzcb: cannot create stream/events on device %d", device_id);
+        delete ctx;
+        cudaGetLastError();
+        return NZCB_E_CUDA;
+    }
+    *out = ctx;
+    return 0;
+}
+
+extern "C" void nzcb_ctx_free(nzcb_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (auto& kv : ctx->twiddles) cudaFree(kv.second);
+    for (auto& kv : ctx->scratch)
+        if (kv.second.first) cudaFree(kv.second.first);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" const char* nzcb_last_error(const nzcb_ctx* ctx) { return ctx ? ctx->err : g_noctx_err; }
+extern "C" uint64_t nzcb_launch_count(const nzcb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" float nzcb_last_device_ms(const nzcb_ctx* ctx) { return ctx ? ctx->last_ms : 0.f; }
+
+extern "C" int32_t nzcb_dev_alloc(nzcb_ctx* ctx, size_t bytes, void** dptr) {
+    if (!ctx || !dptr) return NZCB_E_INVALID;
+    NZ_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (cudaMalloc(dptr, bytes ? bytes : 1) != cudaSuccess) {
+        cudaGetLastError();
+        return ctx->fail(NZCB_E_NOMEM, "cannot allocate %zu device bytes", bytes);
+    }
+    return 0;
+}
+extern "C" int32_t nzcb_dev_free(nzcb_ctx* ctx, void* dptr) {
+    if (!ctx) return NZCB_E_INVALID;
+    NZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    NZ_CUDA(ctx, cudaFree(dptr));
+    return 0;
+}
+extern "C" int32_t nzcb_dev_upload(nzcb_ctx* ctx, void* dptr, const void* host, size_t bytes) {
+    if (!ctx || !dptr || !host) return NZCB_E_INVALID;
+    NZ_CUDA(ctx, cudaMemcpyAsync(dptr, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    NZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+extern "C" int32_t nzcb_dev_download(nzcb_ctx* ctx, void* host, const void* dptr, size_t bytes) {
+    if (!ctx || !dptr || !host) return NZCB_E_INVALID;
+    NZ_CUDA(ctx, cudaMemcpyAsync(host, dptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    NZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}

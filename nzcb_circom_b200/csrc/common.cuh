@@ -1,0 +1,99 @@
+// Context, error plumbing and device workspace shared by every translation unit
+// of libnzcb.so.  One ctx = one GPU = one stream (include/nzcb.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string.h>
+#include <map>
+#include <string>
+#include <vector>
+#include "../../include/nzcb.h"
+#include "g1.cuh"
+
+namespace nzcb {
+struct NttTables;
+struct MsmWorkspace;
+}  // namespace nzcb
+
+struct nzcb_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float last_ms = 0.f;
+    uint64_t launches = 0;
+    char err[512] = {0};
+    // twiddle tables per (log_n, inverse)
+    std::map<uint32_t, nzcb::Fr*> twiddles;
+    // grow-only scratch arenas keyed by name, so steady-state proving never mallocs
+    std::map<std::string, std::pair<void*, size_t>> scratch;
+
+    int fail(int code, const char* fmt, ...) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(err, sizeof(err), fmt, ap);
+        va_end(ap);
+        return code;
+    }
+    // named scratch buffer of at least `bytes`; contents NOT preserved on growth
+    void* scratch_get(const char* name, size_t bytes) {
+        auto& e = scratch[name];
+        if (e.second >= bytes && e.first) return e.first;
+        if (e.first) {
+            cudaStreamSynchronize(stream);
+            cudaFree(e.first);
+            e.first = nullptr;
+            e.second = 0;
+        }
+        void* p = nullptr;
+        size_t want = bytes < 256 ? 256 : bytes;
+        if (cudaMalloc(&p, want) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        e.first = p;
+        e.second = want;
+        return p;
+    }
+};
+
+#define NZ_CUDA(ctx, call)                                                                          \
+    do {                                                                                            \
+        cudaError_t e__ = (call);                                                                   \
+        if (e__ != cudaSuccess)                                                                     \
+            return (ctx)->fail(NZCB_E_CUDA, "CUDA error %s at %s:%d", cudaGetErrorString(e__), __FILE__, \
+                               __LINE__);                                                           \
+    } while (0)
+
+#define NZ_TRY(expr)             \
+    do {                         \
+        int rc__ = (expr);       \
+        if (rc__ != 0) return rc__; \
+    } while (0)
+
+// launch helper: counts launches (bench.py gpu_launches) and checks the launch
+#define NZ_LAUNCH(ctx, kernel, grid, block, smem, ...)                                              \
+    do {                                                                                            \
+        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                            \
+        (ctx)->launches++;                                                                          \
+        cudaError_t e__ = cudaGetLastError();                                                       \
+        if (e__ != cudaSuccess)                                                                     \
+            return (ctx)->fail(NZCB_E_CUDA, "launch of %s failed: %s (%s:%d)", #kernel,             \
+                               cudaGetErrorString(e__), __FILE__, __LINE__);                        \
+    } while (0)
+
+namespace nzcb {
+
+static inline unsigned div_up(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+// --- internal device-level entry points (all asynchronous on ctx->stream) ---
+// ntt.cu
+int ntt_dev(nzcb_ctx* ctx, Fr* d_data, uint32_t log_n, bool inverse);
+// msm.cu : result left in d_out (one G1XYZZ) ; scalars 8 x u32 each
+int msm_dev(nzcb_ctx* ctx, const G1Affine* d_bases, const uint32_t* d_scalars, size_t n, bool scalars_mont,
+            G1XYZZ* d_out);
+int msm_to_host_affine(nzcb_ctx* ctx, const G1XYZZ* d_pt, G1Affine* h_out);
+
+}  // namespace nzcb

@@ -1,0 +1,151 @@
+// Integer-pipe microbenchmarks: the measured denominators of the IMAD roofline
+// ("the 64/clk/SM figure must be confirmed by an IMAD
+// microbenchmark").  kind 0 = IMAD (32x32+32 lo), 1 = IMAD.WIDE.U32 (32x32+64),
+// 2 = Fr Montgomery multiply, 3 = Fq Montgomery multiply.
+#include "common.cuh"
+#include <type_traits>
+
+namespace nzcb {
+
+template <int KIND>
+__global__ void __launch_bounds__(256) k_microbench(uint32_t* out, uint32_t iters, uint32_t seed) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (KIND == 0) {
+        uint32_t a0 = tid * 2654435761u + seed, a1 = a0 ^ 0x9e3779b9u, a2 = a0 + 77u, a3 = a1 + 1234567u;
+        uint32_t a4 = a0 * 3u, a5 = a1 * 5u, a6 = a2 * 7u, a7 = a3 * 11u;
+        const uint32_t m = seed | 1u;
+        for (uint32_t i = 0; i < iters; i++) {
+#pragma unroll
+            for (int u = 0; u < 8; u++) {  // 8 independent chains x 8 = 64 IMAD per iteration
+                a0 = a0 * m + a1; a1 = a1 * m + a2; a2 = a2 * m + a3; a3 = a3 * m + a4;
+                a4 = a4 * m + a5; a5 = a5 * m + a6; a6 = a6 * m + a7; a7 = a7 * m + a0;
+            }
+        }
+        out[tid] = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
+    } else if (KIND == 1) {
+        uint64_t a0 = tid * 2654435761ull + seed, a1 = a0 ^ 0x9e3779b97f4a7c15ull, a2 = a0 + 77u, a3 = a1 + 1234567u;
+        uint64_t a4 = a0 * 3u, a5 = a1 * 5u, a6 = a2 * 7u, a7 = a3 * 11u;
+        const uint32_t m = seed | 1u;
+        for (uint32_t i = 0; i < iters; i++) {
+#pragma unroll
+            for (int u = 0; u < 8; u++) {  // 64 IMAD.WIDE.U32 per iteration
+                a0 = (uint64_t)(uint32_t)a1 * m + a0; a1 = (uint64_t)(uint32_t)a2 * m + a1;
+                a2 = (uint64_t)(uint32_t)a3 * m + a2; a3 = (uint64_t)(uint32_t)a4 * m + a3;
+                a4 = (uint64_t)(uint32_t)a5 * m + a4; a5 = (uint64_t)(uint32_t)a6 * m + a5;
+                a6 = (uint64_t)(uint32_t)a7 * m + a6; a7 = (uint64_t)(uint32_t)a0 * m + a7;
+            }
+        }
+        uint64_t x = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
+        out[tid] = (uint32_t)x ^ (uint32_t)(x >> 32);
+    } else if (KIND == 4) {
+        uint32_t a0 = tid * 2654435761u + seed, a1 = a0 ^ 0x9e3779b9u, a2 = a0 + 77u, a3 = a1 + 1234567u;
+        uint32_t a4 = a0 * 3u, a5 = a1 * 5u, a6 = a2 * 7u, a7 = a3 * 11u;
+        const uint32_t m = seed | 0x80000001u;
+        for (uint32_t i = 0; i < iters; i++) {
+#pragma unroll
+            for (int u = 0; u < 8; u++) {  // 64 IMAD.HI.U32 per iteration
+                a0 = __umulhi(a0, m) + a1; a1 = __umulhi(a1, m) + a2; a2 = __umulhi(a2, m) + a3; a3 = __umulhi(a3, m) + a4;
+                a4 = __umulhi(a4, m) + a5; a5 = __umulhi(a5, m) + a6; a6 = __umulhi(a6, m) + a7; a7 = __umulhi(a7, m) + a0;
+            }
+        }
+        out[tid] = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
+    } else if (KIND == 5) {
+        Fr a = Fr::from_u64(tid + 3), b = Fr::from_u64(seed + 5), c = Fr::from_u64(tid * 7 + 1), d = Fr::from_u64(seed * 3 + 11);
+        for (uint32_t i = 0; i < iters; i++) {
+            a = Fr::mul_portable(a, b);
+            c = Fr::mul_portable(c, d);
+            b = Fr::mul_portable(b, a);
+            d = Fr::mul_portable(d, c);
+        }
+        Fr r = a + b + c + d;
+        uint32_t x = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) x ^= r.v[k];
+        out[tid] = x;
+    } else {
+        typedef typename std::conditional<KIND == 2, Fr, Fq>::type F;
+        F a = F::from_u64(tid + 3), b = F::from_u64(seed + 5), c = F::from_u64(tid * 7 + 1), d = F::from_u64(seed * 3 + 11);
+        for (uint32_t i = 0; i < iters; i++) {  // 4 multiplies per iteration, two independent chains
+            a = a * b;
+            c = c * d;
+            b = b * a;
+            d = d * c;
+        }
+        F r = a + b + c + d;
+        uint32_t x = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) x ^= r.v[k];
+        out[tid] = x;
+    }
+}
+
+
+// device self-test: the carry-chain multiply must agree bit-for-bit with the portable CIOS
+template <class F>
+__global__ void k_selftest_mul(uint32_t n, uint32_t seed, unsigned long long* mismatches) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= n) return;
+    F a, b;
+    uint32_t x = tid * 747796405u + seed;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        x = x * 1664525u + 1013904223u; a.v[k] = x ^ (x >> 15);
+        x = x * 1664525u + 1013904223u; b.v[k] = x ^ (x >> 13);
+    }
+    a.v[7] &= 0x1fffffffu; b.v[7] &= 0x1fffffffu;  // < 2^253 < modulus
+    if (tid == 0) { a = F::zero(); }
+    if (tid == 1) { a = F::modulus(); a.v[0] -= 1; b = a; }
+    F acc_p = a, acc_q = a;
+    unsigned long long bad = 0;
+    for (int it = 0; it < 16; it++) {
+        F p = F::mul_portable(acc_p, b);
+        F q = acc_q * b;
+        if (p != q) bad++;
+        acc_p = p; acc_q = q;
+        b = b + acc_p;
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+}  // namespace nzcb
+using namespace nzcb;
+
+extern "C" int32_t nzcb_selftest_mul(nzcb_ctx* ctx, uint32_t n, uint64_t* mismatches) {
+    if (!ctx || !mismatches) return NZCB_E_INVALID;
+    unsigned long long* d = (unsigned long long*)ctx->scratch_get("selftest", 8);
+    if (!d) return ctx->fail(NZCB_E_NOMEM, "selftest: out of memory");
+    NZ_CUDA(ctx, cudaMemsetAsync(d, 0, 8, ctx->stream));
+    NZ_LAUNCH(ctx, k_selftest_mul<Fr>, div_up(n, 256), 256, 0, n, 17u, d);
+    NZ_LAUNCH(ctx, k_selftest_mul<Fq>, div_up(n, 256), 256, 0, n, 29u, d);
+    unsigned long long h = 0;
+    NZ_CUDA(ctx, cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    NZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *mismatches = h;
+    return 0;
+}
+
+
+// returns operations per second in *ops_per_s (IMAD / IMAD.WIDE / modmul), device time in ctx->last_ms
+extern "C" int32_t nzcb_microbench(nzcb_ctx* ctx, int32_t kind, uint32_t iters, uint32_t blocks_per_sm,
+                                   double* ops_per_s) {
+    if (!ctx || !ops_per_s || kind < 0 || kind > 5) return NZCB_E_INVALID;
+    const uint32_t grid = (uint32_t)ctx->sm_count * (blocks_per_sm ? blocks_per_sm : 4);
+    uint32_t* d = (uint32_t*)ctx->scratch_get("microbench", (size_t)grid * 256 * 4);
+    if (!d) return ctx->fail(NZCB_E_NOMEM, "microbench: out of memory");
+    for (int rep = 0; rep < 2; rep++) {  // first repetition is the warm-up
+        NZ_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+        switch (kind) {
+            case 0: NZ_LAUNCH(ctx, k_microbench<0>, grid, 256, 0, d, iters, 12345u); break;
+            case 1: NZ_LAUNCH(ctx, k_microbench<1>, grid, 256, 0, d, iters, 12345u); break;
+            case 2: NZ_LAUNCH(ctx, k_microbench<2>, grid, 256, 0, d, iters, 12345u); break;
+            case 3: NZ_LAUNCH(ctx, k_microbench<3>, grid, 256, 0, d, iters, 12345u); break;
+            case 4: NZ_LAUNCH(ctx, k_microbench<4>, grid, 256, 0, d, iters, 12345u); break;
+            default: NZ_LAUNCH(ctx, k_microbench<5>, grid, 256, 0, d, iters, 12345u); break;
+        }
+        NZ_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+        NZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1);
+    const double per_thread = (kind <= 1 || kind == 4) ? 64.0 * iters : 4.0 * iters;
+    *ops_per_s = per_thread * grid * 256.0 / (ctx->last_ms * 1e-3);
+    return 0;
+}

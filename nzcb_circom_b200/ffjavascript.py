@@ -1,0 +1,50 @@
+"""Host mirror of the two ffjavascript 0.2.48 primitives on the proving path
+(un-vendored dependency, /root/reference/yarn.lock:3905):
+
+    curve.Fr.fft(buff) / curve.Fr.ifft(buff)     -> Fr.fft / Fr.ifft
+    curve.G1.multiExpAffine(buffBases, buffScalars) -> G1.multiExpAffine
+
+Same buffer conventions as the JS: field elements 32-byte little-endian
+Montgomery, G1 affine 64 bytes, scalars 32-byte little-endian canonical.
+Everything runs in libnzcb.so on the GPU."""
+import ctypes
+
+from ._lib import default_context
+
+
+class _Fr:
+    n8 = 32
+
+    def fft(self, buff, ctx=None):
+        return self._ntt(buff, 0, ctx)
+
+    def ifft(self, buff, ctx=None):
+        return self._ntt(buff, 1, ctx)
+
+    @staticmethod
+    def _ntt(buff, inverse, ctx):
+        ctx = ctx or default_context()
+        n = len(buff) // 32
+        if n * 32 != len(buff) or n & (n - 1) or n == 0:
+            raise ValueError("Size must be multiple of 2")  # ffjavascript's message
+        log_n = n.bit_length() - 1
+        data = (ctypes.c_uint8 * len(buff)).from_buffer_copy(buff)
+        ctx.check(ctx.lib.nzcb_ntt_fr(ctx.h, data, log_n, inverse))
+        return bytes(data)
+
+
+class _G1:
+    def multiExpAffine(self, buffBases, buffScalars, ctx=None):
+        ctx = ctx or default_context()
+        n = len(buffBases) // 64
+        if len(buffScalars) != n * 32:
+            raise ValueError("Number of scalars does not match number of bases")
+        out = (ctypes.c_uint8 * 64)()
+        b = (ctypes.c_uint8 * max(1, len(buffBases))).from_buffer_copy(buffBases or b"\0")
+        s = (ctypes.c_uint8 * max(1, len(buffScalars))).from_buffer_copy(buffScalars or b"\0")
+        ctx.check(ctx.lib.nzcb_msm_g1(ctx.h, b, s, n, out))
+        return bytes(out)
+
+
+Fr = _Fr()
+G1 = _G1()

@@ -1,0 +1,107 @@
+"""Config 3 (primitive sweep) parity: BN254 Fr NTT and G1 MSM through the C ABI
+vs. the Python big-int oracle (bit-exact), plus size-independent algebraic
+properties at the BASELINE.json sizes.  SURVEY.md section 4 (v)."""
+import random
+
+import pytest
+
+from oracle import bn254 as b
+from oracle import ntt as ontt
+
+pytestmark = pytest.mark.gpu
+
+
+def _fr_buf(vals):
+    return b"".join(b.to_lem(v) for v in vals)
+
+
+def _fr_unbuf(buf):
+    return [b.from_lem(buf[i:i + 32]) for i in range(0, len(buf), 32)]
+
+
+@pytest.mark.parametrize("log_n", [1, 2, 3, 4, 5, 6, 7, 9, 10, 12])
+def test_ntt_matches_oracle(ctx, log_n):
+    from nzcb_circom_b200.ffjavascript import Fr
+
+    rng = random.Random(0x6E7A6362 + log_n)
+    vals = [rng.randrange(b.R_MOD) for _ in range(1 << log_n)]
+    vals[0] = 0
+    vals[-1] = b.R_MOD - 1
+    got = _fr_unbuf(Fr.fft(_fr_buf(vals), ctx))
+    assert got == ontt.fft(vals)
+    got_i = _fr_unbuf(Fr.ifft(_fr_buf(vals), ctx))
+    assert got_i == ontt.ifft(vals)
+
+
+@pytest.mark.parametrize("log_n", [16, 20, 22])
+def test_ntt_roundtrip_and_pointcheck_large(ctx, log_n):
+    """iNTT(NTT(x)) == x bit-exact, and X[k] == sum_j x_j w^(jk) for a sparse x."""
+    import numpy as np
+    from nzcb_circom_b200.ffjavascript import Fr
+
+    n = 1 << log_n
+    rng = np.random.default_rng(log_n)
+    raw = rng.integers(0, 256, size=n * 32, dtype=np.uint8)
+    raw.reshape(n, 32)[:, 31] &= 0x1F  # < 2^253 < r: valid (arbitrary) Montgomery residues
+    buf = raw.tobytes()
+    fwd = Fr.fft(buf, ctx)
+    assert Fr.ifft(fwd, ctx) == buf
+    # sparse input: three non-zero coefficients -> closed form at a few output points
+    idx = [0, 5, n - 3]
+    coef = [7, b.R_MOD - 2, 123456789]
+    sp = bytearray(n * 32)
+    for i, c in zip(idx, coef):
+        sp[i * 32:(i + 1) * 32] = b.to_lem(c)
+    out = Fr.fft(bytes(sp), ctx)
+    w = b.fr_root(log_n)
+    for k in [0, 1, 2, n // 2 + 1, n - 1, 12345 % n]:
+        exp = sum(c * pow(w, i * k, b.R_MOD) for i, c in zip(idx, coef)) % b.R_MOD
+        assert b.from_lem(out[k * 32:(k + 1) * 32]) == exp
+
+
+def _points(rng, n):
+    # distinct multiples of G, built incrementally (cheap in Python)
+    pts = []
+    P = b.g1_mul(b.G1_GEN, rng.randrange(1, b.R_MOD))
+    step = b.g1_mul(b.G1_GEN, rng.randrange(1, b.R_MOD))
+    for _ in range(n):
+        pts.append(P)
+        P = b.g1_add(P, step)
+    return pts
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 31, 33, 100, 1000, 5000])
+def test_msm_matches_oracle(ctx, n):
+    from nzcb_circom_b200.ffjavascript import G1
+
+    rng = random.Random(n + 1)
+    pts = _points(rng, n)
+    sc = [rng.randrange(b.R_MOD) for _ in range(n)]
+    if n >= 3:
+        sc[0] = 0
+        sc[1] = b.R_MOD - 1
+        sc[2] = 1
+    if n >= 33:
+        pts[5] = None  # infinity base (all-zero bytes)
+        pts[7] = pts[6]  # equal bases -> doubling path when scalars collide
+        sc[7] = sc[6]
+        pts[9] = b.g1_neg(pts[8])  # cancelling pair
+        sc[9] = sc[8]
+    bases = b"".join(b.g1_to_lem(P) for P in pts)
+    scal = b"".join(b.to_le(s) for s in sc)
+    got = b.g1_from_lem(G1.multiExpAffine(bases, scal, ctx))
+    assert got == b.g1_msm(pts, sc)
+
+
+def test_msm_small_scalars(ctx):
+    """0/1/byte scalars (what wire values look like): heavy bucket imbalance."""
+    from nzcb_circom_b200.ffjavascript import G1
+
+    rng = random.Random(99)
+    n = 4096
+    pts = _points(rng, n)
+    sc = [rng.choice([0, 1, 1, 1, rng.randrange(256)]) for _ in range(n)]
+    bases = b"".join(b.g1_to_lem(P) for P in pts)
+    scal = b"".join(b.to_le(s) for s in sc)
+    got = b.g1_from_lem(G1.multiExpAffine(bases, scal, ctx))
+    assert got == b.g1_msm(pts, sc)
