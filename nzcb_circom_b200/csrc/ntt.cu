@@ -14,6 +14,7 @@
 // Roofline: (N/2) log2 N modmul = 132 N log2 N IMAD32; HBM traffic
 // is 64 N bytes per pass, ceil(log2 N / 3) + 1 passes -- integer-pipe bound.
 #include "common.cuh"
+#include "poly.cuh"
 
 namespace nzcb {
 
@@ -91,7 +92,7 @@ Fr fr_root_host(uint32_t log_n) {
     return w;
 }
 
-static int get_twiddles(nzcb_ctx* ctx, uint32_t log_n, bool inverse, const Fr** out) {
+int get_twiddles_pub(nzcb_ctx* ctx, uint32_t log_n, bool inverse, const Fr** out) {
     const uint32_t key = log_n * 2 + (inverse ? 1 : 0);
     auto it = ctx->twiddles.find(key);
     if (it != ctx->twiddles.end()) {
@@ -113,7 +114,7 @@ int ntt_dev(nzcb_ctx* ctx, Fr* d, uint32_t log_n, bool inverse) {
     if (log_n > 28) return ctx->fail(NZCB_E_INVALID, "ntt: log_n %u exceeds the 2-adicity of Fr (28)", log_n);
     if (log_n == 0) return 0;
     const Fr* W = nullptr;
-    NZ_TRY(get_twiddles(ctx, log_n, inverse, &W));
+    NZ_TRY(get_twiddles_pub(ctx, log_n, inverse, &W));
     uint32_t s = 0;
     const uint32_t rem = log_n % 3;
     if (rem == 1) {

@@ -1,0 +1,916 @@
+// PLONK prover -- replaces snarkjs 0.4.12 plonk.prove(zkey, wtns) (un-vendored,
+// /root/reference/yarn.lock:7279; the reference only names it in its Makefile
+// recipe, /root/reference/Makefile:54-62).  Data flow and transcript follow
+// SURVEY.md A.2 step by step so that, with the nine blinders injected, the proof
+// is the same 800 bytes snarkjs would print; the JS loops become kernels:
+//   witness -> Montgomery, additions level by level, A/B/C gather       (round 1)
+//   grand product: fused num/den, batch inverse, prefix-product scan     (round 2)
+//   quotient T / Tz: one fused elementwise kernel over the 4n domain     (round 3)
+//   evalPol / divPol1: segmented Horner scans (poly.cu)                  (rounds 4, 5)
+// The zkey is parsed once and stays device resident in Montgomery form.
+#include "common.cuh"
+#include "keccak.h"
+#include "poly.cuh"
+#include <algorithm>
+
+using namespace nzcb;
+
+struct nzcb_zkey {
+    nzcb_ctx* ctx = nullptr;
+    uint32_t n_vars = 0, n_public = 0, n = 0, power = 0, n_add = 0, n_cons = 0;
+    Fr k1, k2;
+    uint32_t* d_map[3] = {nullptr, nullptr, nullptr};
+    // additions sorted by dependency level
+    uint32_t *d_add_a = nullptr, *d_add_b = nullptr, *d_add_out = nullptr;
+    Fr *d_add_ac = nullptr, *d_add_bc = nullptr;
+    std::vector<uint32_t> level_off;  // additions of level l are [level_off[l], level_off[l+1])
+    Fr* d_q[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // n coefs then 4n evals each
+    Fr* d_sigma = nullptr;                                       // 3 x (n + 4n)
+    Fr* d_lag = nullptr;                                         // max(nPublic,1) x (n + 4n)
+    G1Affine* d_ptau = nullptr;                                  // n + 6
+};
+
+namespace {
+
+struct Section {
+    const uint8_t* p;
+    uint64_t size;
+};
+
+int parse_binfile(nzcb_ctx* ctx, const uint8_t* data, size_t len, const char* magic, std::map<uint32_t, Section>& out) {
+    if (len < 12 || memcmp(data, magic, 4) != 0) return ctx->fail(NZCB_E_INVALID, "%s file: bad magic", magic);
+    uint32_t nsec;
+    memcpy(&nsec, data + 8, 4);
+    size_t pos = 12;
+    for (uint32_t i = 0; i < nsec; i++) {
+        if (pos + 12 > len) return ctx->fail(NZCB_E_INVALID, "%s file: truncated section table", magic);
+        uint32_t id;
+        uint64_t size;
+        memcpy(&id, data + pos, 4);
+        memcpy(&size, data + pos + 4, 8);
+        pos += 12;
+        if (pos + size > len) return ctx->fail(NZCB_E_INVALID, "%s file: section %u overruns the file", magic, id);
+        if (!out.count(id)) out[id] = Section{data + pos, size};
+        pos += size;
+    }
+    return 0;
+}
+
+const uint8_t R_LE[32] = {0x01, 0x00, 0x00, 0xf0, 0x93, 0xf5, 0xe1, 0x43, 0x91, 0x70, 0xb9, 0x79, 0x48, 0xe8, 0x33, 0x28,
+                          0x5d, 0x58, 0x81, 0x81, 0xb6, 0x45, 0x50, 0xb8, 0x29, 0xa0, 0x31, 0xe1, 0x72, 0x4e, 0x64, 0x30};
+const uint8_t Q_LE[32] = {0x47, 0xfd, 0x7c, 0xd8, 0x16, 0x8c, 0x20, 0x3c, 0x8d, 0xca, 0x71, 0x68, 0x91, 0x6a, 0x81, 0x97,
+                          0x5d, 0x58, 0x81, 0x81, 0xb6, 0x45, 0x50, 0xb8, 0x29, 0xa0, 0x31, 0xe1, 0x72, 0x4e, 0x64, 0x30};
+
+template <class F>
+void to_be_bytes(const F& mont, uint8_t out[32]) {
+    F c = mont.from_mont();
+    for (int i = 0; i < 8; i++)
+        for (int k = 0; k < 4; k++) out[31 - (4 * i + k)] = (uint8_t)(c.v[i] >> (8 * k));
+}
+void g1_to_be(const G1Affine& p, uint8_t out[64]) {
+    to_be_bytes(p.x, out);
+    to_be_bytes(p.y, out + 32);
+}
+// snarkjs hashToFr: keccak256 digest as a big-endian integer, reduced mod r; returned in Montgomery form
+Fr hash_to_fr(const std::vector<uint8_t>& msg) {
+    uint8_t dg[32];
+    keccak256(msg.data(), msg.size(), dg);
+    Fr v;
+    for (int i = 0; i < 8; i++) {
+        uint32_t w = 0;
+        for (int k = 0; k < 4; k++) w |= (uint32_t)dg[31 - (4 * i + k)] << (8 * k);
+        v.v[i] = w;
+    }
+    // v < 2^256 < 6r: subtract r while v >= r
+    for (int it = 0; it < 6; it++) {
+        uint32_t t[8];
+        uint32_t borrow = 0;
+        for (int i = 0; i < 8; i++) {
+            uint64_t d = (uint64_t)v.v[i] - FrParams::mod(i) - borrow;
+            t[i] = (uint32_t)d;
+            borrow = (uint32_t)(d >> 63);
+        }
+        if (borrow) break;
+        for (int i = 0; i < 8; i++) v.v[i] = t[i];
+    }
+    return v.to_mont();
+}
+void append(std::vector<uint8_t>& v, const uint8_t* p, size_t n) { v.insert(v.end(), p, p + n); }
+
+// ---------------------------------------------------------------- kernels
+__global__ void k_wtns_to_mont(const Fr* __restrict__ w_le, Fr* __restrict__ W, size_t n_w) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_w) return;
+    // "First element in plonk is not used ... We set it to zero" (A.2 step 0)
+    W[i] = i == 0 ? Fr::zero() : w_le[i].to_mont();
+}
+
+__global__ void k_additions(const uint32_t* __restrict__ ia, const uint32_t* __restrict__ ib,
+                            const Fr* __restrict__ ac, const Fr* __restrict__ bc, const uint32_t* __restrict__ iout,
+                            uint32_t lo, uint32_t hi, uint32_t n_vars, uint32_t n_w, Fr* __restrict__ W) {
+    const uint32_t i = lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= hi) return;
+    const uint32_t a = ia[i], b = ib[i];
+    const Fr aw = a < n_vars ? W[a] : Fr::zero();
+    const Fr bw = b < n_vars ? W[b] : Fr::zero();
+    W[n_w + iout[i]] = ac[i] * aw + bc[i] * bw;
+}
+
+__global__ void k_gather(const uint32_t* __restrict__ map, const Fr* __restrict__ W, uint32_t n_vars, uint32_t n_cons,
+                         uint32_t n, Fr* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr v = Fr::zero();
+    if (i < n_cons) {
+        const uint32_t s = map[i];
+        if (s < n_vars) v = W[s];
+    }
+    out[i] = v;
+}
+
+// dst[0..n) = src, dst[n..total) = 0
+__global__ void k_copy_pad(const Fr* __restrict__ src, size_t n, Fr* __restrict__ dst, size_t total) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    dst[i] = i < n ? src[i] : Fr::zero();
+}
+
+// pol (n + k coefficients) = coef + (pz[0] + pz[1] X + ...) * (X^n - 1)      (to4T, A.2 round 1)
+struct Blind {
+    Fr pz[3];
+    int k;
+};
+__global__ void k_blind(Fr* __restrict__ pol, size_t n, Blind bl) {
+    const int j = threadIdx.x;
+    if (j >= bl.k) return;
+    pol[n + j] = bl.pz[j];
+    pol[j] = pol[j] - bl.pz[j];
+}
+
+struct R2Args {
+    const Fr *A, *B, *C, *S14, *S24, *S34, *Wn;
+    Fr beta, gamma, k1, k2;
+    uint32_t n, power;
+    Fr *num, *den;
+};
+__global__ void __launch_bounds__(128) k_round2_terms(R2Args a) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const Fr w = domain_pow(a.Wn, a.power, i);
+    const Fr bw = a.beta * w;
+    const Fr av = a.A[i], bv = a.B[i], cv = a.C[i];
+    const Fr n1 = av + bw + a.gamma;
+    const Fr n2 = bv + a.k1 * bw + a.gamma;
+    const Fr n3 = cv + a.k2 * bw + a.gamma;
+    a.num[i] = n1 * (n2 * n3);
+    const Fr d1 = av + a.S14[(size_t)4 * i] * a.beta + a.gamma;
+    const Fr d2 = bv + a.S24[(size_t)4 * i] * a.beta + a.gamma;
+    const Fr d3 = cv + a.S34[(size_t)4 * i] * a.beta + a.gamma;
+    a.den[i] = d1 * (d2 * d3);
+}
+
+__global__ void k_mul_inplace(Fr* __restrict__ a, const Fr* __restrict__ b, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    a[i] = a[i] * b[i];
+}
+
+struct R3Args {
+    const Fr *A4, *B4, *C4, *Z4, *QM4, *QL4, *QR4, *QO4, *QC4, *S14, *S24, *S34, *L4, *pub, *W4n;
+    Fr b[10];
+    Fr beta, gamma, alpha, alpha2, k1, k2, wn;
+    Fr Z1[4], Z2[4], Z3[4];
+    uint32_t n, power, n_pub;
+    Fr *T, *Tz;
+};
+
+struct Pair {
+    Fr r, rz;
+};
+// (a + Zh ap)(b + Zh bp)(c + Zh cp)(d + Zh dp) split into the Zh-free part r and the cofactor of Zh, rz
+__device__ __forceinline__ Pair mul4(const Fr& a, const Fr& b, const Fr& c, const Fr& d, const Fr& ap, const Fr& bp,
+                                     const Fr& cp, const Fr& dp, const Fr& ap_bp, const Fr& z1, const Fr& z2,
+                                     const Fr& z3, bool on_domain) {
+    const Fr a_b = a * b, c_d = c * d;
+    const Fr ab1 = a * bp + ap * b;   // a_bp + ap_b
+    const Fr cd1 = c * dp + cp * d;   // c_dp + cp_d
+    const Fr cp_dp = cp * dp;
+    Pair o;
+    o.r = a_b * c_d;
+    const Fr a0 = ab1 * c_d + a_b * cd1;
+    if (on_domain) {  // Zh = 0 on every 4th point
+        o.rz = a0;
+        return o;
+    }
+    const Fr a1 = ap_bp * c_d + ab1 * cd1 + a_b * cp_dp;
+    const Fr a2 = ab1 * cp_dp + ap_bp * cd1;
+    const Fr a3 = ap_bp * cp_dp;
+    o.rz = a0 + z1 * a1 + z2 * a2 + z3 * a3;
+    return o;
+}
+
+__global__ void __launch_bounds__(128) k_round3(R3Args g) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t n4 = (size_t)4 * g.n;
+    if (i >= n4) return;
+    const uint32_t p = (uint32_t)(i & 3);
+    const Fr x = domain_pow(g.W4n, g.power + 2, i);
+    const Fr a = g.A4[i], b = g.B4[i], c = g.C4[i], z = g.Z4[i];
+    const Fr zw = g.Z4[(i + 4) & (n4 - 1)];
+    const Fr ap = g.b[2] + g.b[1] * x;
+    const Fr bp = g.b[4] + g.b[3] * x;
+    const Fr cp = g.b[6] + g.b[5] * x;
+    const Fr zp = (g.b[7] * x + g.b[8]) * x + g.b[9];
+    const Fr xw = x * g.wn;
+    const Fr zwp = (g.b[7] * xw + g.b[8]) * xw + g.b[9];
+    const Fr l1 = g.L4[(size_t)g.n + i];
+
+    Fr pl = Fr::zero();
+    for (uint32_t j = 0; j < g.n_pub; j++) pl = pl - g.L4[(size_t)j * 5 * g.n + g.n + i] * g.pub[j];
+
+    const Fr z1 = g.Z1[p], z2 = g.Z2[p], z3 = g.Z3[p];
+    const Fr ap_bp = ap * bp;
+    // gate part
+    const Fr qm = g.QM4[i], ql = g.QL4[i], qr = g.QR4[i], qo = g.QO4[i], qc = g.QC4[i];
+    Fr e1 = (a * b) * qm + a * ql + b * qr + c * qo + pl + qc;
+    Fr e1z = (a * bp + ap * b + z1 * ap_bp) * qm + ap * ql + bp * qr + cp * qo;
+    // permutation parts
+    const Fr bx = g.beta * x;
+    const Pair e2 = mul4(a + bx + g.gamma, b + bx * g.k1 + g.gamma, c + bx * g.k2 + g.gamma, z, ap, bp, cp, zp, ap_bp,
+                         z1, z2, z3, p == 0);
+    const Pair e3 = mul4(a + g.beta * g.S14[i] + g.gamma, b + g.beta * g.S24[i] + g.gamma,
+                         c + g.beta * g.S34[i] + g.gamma, zw, ap, bp, cp, zwp, ap_bp, z1, z2, z3, p == 0);
+    const Fr e4 = (z - Fr::one()) * l1 * g.alpha2;
+    const Fr e4z = zp * l1 * g.alpha2;
+    g.T[i] = e1 + (e2.r - e3.r) * g.alpha + e4;
+    g.Tz[i] = e1z + (e2.rz - e3.rz) * g.alpha + e4z;
+}
+
+// t /= Z_H in coefficient space (A.2 round 3); flags[0] set if a coefficient above 3n-4 is non-zero
+__global__ void k_div_zh(Fr* __restrict__ t, uint32_t n, int* __restrict__ flags) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr prev = t[i].neg();
+    t[i] = prev;
+    for (uint32_t k = 1; k < 4; k++) {
+        const size_t idx = (size_t)k * n + i;
+        prev = prev - t[idx];
+        t[idx] = prev;
+        if (idx > (size_t)3 * n - 4 && !prev.is_zero()) atomicOr(&flags[0], 1);
+    }
+}
+// t += tz (i <= 3n+5), tz must vanish above; flags[1]
+__global__ void k_add_tz(Fr* __restrict__ t, const Fr* __restrict__ tz, uint32_t n, int* __restrict__ flags) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)4 * n) return;
+    const Fr v = tz[i];
+    if (i > (size_t)3 * n + 5) {
+        if (!v.is_zero()) atomicOr(&flags[1], 1);
+    } else {
+        t[i] = t[i] + v;
+    }
+}
+
+struct R4Args {
+    const Fr *pol_z, *qm, *ql, *qr, *qo, *qc, *s3;
+    Fr coefz, coef_ab, ea, eb, ec, e3;
+    uint32_t n;
+    Fr* pol_r;
+};
+__global__ void k_pol_r(R4Args g) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= g.n + 3) return;
+    Fr v = g.coefz * g.pol_z[i];
+    if (i < g.n)
+        v = v + g.coef_ab * g.qm[i] + g.ea * g.ql[i] + g.eb * g.qr[i] + g.ec * g.qo[i] + g.qc[i] - g.e3 * g.s3[i];
+    g.pol_r[i] = v;
+}
+
+struct R5Args {
+    const Fr *pol_t, *pol_r, *pol_a, *pol_b, *pol_c, *s1, *s2;
+    Fr xim, xi2m, v[7], w0_sub;
+    uint32_t n;
+    Fr* out;
+};
+__global__ void k_pol_wxi(R5Args g) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n = g.n;
+    if (i >= n + 6) return;
+    Fr w = g.xi2m * g.pol_t[(size_t)2 * n + i];
+    if (i < n + 3) w = w + g.v[1] * g.pol_r[i];
+    if (i < n + 2) w = w + g.v[2] * g.pol_a[i] + g.v[3] * g.pol_b[i] + g.v[4] * g.pol_c[i];
+    if (i < n) w = w + g.pol_t[i] + g.xim * g.pol_t[(size_t)n + i] + g.v[5] * g.s1[i] + g.v[6] * g.s2[i];
+    if (i == 0) w = w - g.w0_sub;
+    g.out[i] = w;
+}
+__global__ void k_sub_at0(Fr* p, Fr v) { p[0] = p[0] - v; }
+
+Fr fr_from_le(const uint8_t* p) {
+    Fr f;
+    memcpy(f.v, p, 32);
+    return f;
+}
+bool fr_is_canonical(const Fr& f) {
+    for (int i = 7; i >= 0; i--) {
+        if (f.v[i] < FrParams::mod(i)) return true;
+        if (f.v[i] > FrParams::mod(i)) return false;
+    }
+    return false;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ zkey load
+extern "C" void nzcb_zkey_free(nzcb_zkey* zk) {
+    if (!zk) return;
+    if (zk->ctx) {
+        cudaSetDevice(zk->ctx->device);
+        cudaStreamSynchronize(zk->ctx->stream);
+    }
+    for (int i = 0; i < 3; i++) cudaFree(zk->d_map[i]);
+    cudaFree(zk->d_add_a);
+    cudaFree(zk->d_add_b);
+    cudaFree(zk->d_add_out);
+    cudaFree(zk->d_add_ac);
+    cudaFree(zk->d_add_bc);
+    for (int i = 0; i < 5; i++) cudaFree(zk->d_q[i]);
+    cudaFree(zk->d_sigma);
+    cudaFree(zk->d_lag);
+    cudaFree(zk->d_ptau);
+    delete zk;
+}
+
+extern "C" int32_t nzcb_zkey_info(const nzcb_zkey* zk, uint32_t* n_vars, uint32_t* n_public, uint32_t* domain_size,
+                                  uint32_t* n_additions, uint32_t* n_constraints) {
+    if (!zk) return NZCB_E_INVALID;
+    if (n_vars) *n_vars = zk->n_vars;
+    if (n_public) *n_public = zk->n_public;
+    if (domain_size) *domain_size = zk->n;
+    if (n_additions) *n_additions = zk->n_add;
+    if (n_constraints) *n_constraints = zk->n_cons;
+    return 0;
+}
+
+#define ZK_CUDA(call)                                                                                      \
+    do {                                                                                                   \
+        cudaError_t e__ = (call);                                                                          \
+        if (e__ != cudaSuccess) {                                                                          \
+            ctx->fail(NZCB_E_CUDA, "CUDA error %s at %s:%d", cudaGetErrorString(e__), __FILE__, __LINE__); \
+            nzcb_zkey_free(zk);                                                                            \
+            return NZCB_E_CUDA;                                                                            \
+        }                                                                                                  \
+    } while (0)
+
+extern "C" int32_t nzcb_zkey_load(nzcb_ctx* ctx, const uint8_t* data, size_t len, nzcb_zkey** out) {
+    if (!ctx || !data || !out) return NZCB_E_INVALID;
+    *out = nullptr;
+    std::map<uint32_t, Section> sec;
+    NZ_TRY(parse_binfile(ctx, data, len, "zkey", sec));
+    for (uint32_t id = 1; id <= 14; id++)
+        if (!sec.count(id)) return ctx->fail(NZCB_E_INVALID, "zkey file: section %u missing", id);
+    uint32_t proto = 0;
+    if (sec[1].size < 4) return ctx->fail(NZCB_E_INVALID, "zkey file: bad section 1");
+    memcpy(&proto, sec[1].p, 4);
+    if (proto != 2) return ctx->fail(NZCB_E_INVALID, "zkey file is not plonk");
+    const uint8_t* h = sec[2].p;
+    if (sec[2].size < 4 + 32 + 4 + 32 + 20 + 64 + 8 * 64 + 128) return ctx->fail(NZCB_E_INVALID, "zkey file: short header");
+    uint32_t n8q, n8r;
+    memcpy(&n8q, h, 4);
+    memcpy(&n8r, h + 36, 4);
+    if (n8q != 32 || n8r != 32 || memcmp(h + 4, Q_LE, 32) != 0 || memcmp(h + 40, R_LE, 32) != 0)
+        return ctx->fail(NZCB_E_INVALID, "zkey file: curve is not bn128");
+    nzcb_zkey* zk = new nzcb_zkey();
+    zk->ctx = ctx;
+    uint32_t f[5];
+    memcpy(f, h + 72, 20);
+    zk->n_vars = f[0];
+    zk->n_public = f[1];
+    zk->n = f[2];
+    zk->n_add = f[3];
+    zk->n_cons = f[4];
+    memcpy(zk->k1.v, h + 92, 32);
+    memcpy(zk->k2.v, h + 124, 32);
+    const uint64_t n = zk->n;
+    if (n < 8 || (n & (n - 1)) || zk->n_cons > n || zk->n_add > zk->n_vars) {
+        delete zk;
+        return ctx->fail(NZCB_E_INVALID, "zkey file: inconsistent header (domainSize %u, nConstraints %u)", (unsigned)n,
+                         f[4]);
+    }
+    zk->power = 0;
+    while (((uint64_t)1 << zk->power) < n) zk->power++;
+    const uint32_t n_lag = zk->n_public > 1 ? zk->n_public : 1;
+    bool ok = sec[3].size == (uint64_t)zk->n_add * 72;
+    for (int c = 0; c < 3; c++) ok = ok && sec[4 + c].size == (uint64_t)zk->n_cons * 4;
+    for (int k = 0; k < 5; k++) ok = ok && sec[7 + k].size == 5 * n * 32;
+    ok = ok && sec[12].size == 15 * n * 32 && sec[13].size == (uint64_t)n_lag * 5 * n * 32 && sec[14].size == (n + 6) * 64;
+    if (!ok) {
+        delete zk;
+        return ctx->fail(NZCB_E_INVALID, "zkey file: section sizes do not match the header");
+    }
+    ZK_CUDA(cudaSetDevice(ctx->device));
+    for (int c = 0; c < 3; c++) {
+        ZK_CUDA(cudaMalloc(&zk->d_map[c], std::max<size_t>(4, sec[4 + c].size)));
+        ZK_CUDA(cudaMemcpyAsync(zk->d_map[c], sec[4 + c].p, sec[4 + c].size, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    for (int k = 0; k < 5; k++) {
+        ZK_CUDA(cudaMalloc(&zk->d_q[k], sec[7 + k].size));
+        ZK_CUDA(cudaMemcpyAsync(zk->d_q[k], sec[7 + k].p, sec[7 + k].size, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    ZK_CUDA(cudaMalloc(&zk->d_sigma, sec[12].size));
+    ZK_CUDA(cudaMemcpyAsync(zk->d_sigma, sec[12].p, sec[12].size, cudaMemcpyHostToDevice, ctx->stream));
+    ZK_CUDA(cudaMalloc(&zk->d_lag, sec[13].size));
+    ZK_CUDA(cudaMemcpyAsync(zk->d_lag, sec[13].p, sec[13].size, cudaMemcpyHostToDevice, ctx->stream));
+    ZK_CUDA(cudaMalloc(&zk->d_ptau, sec[14].size));
+    ZK_CUDA(cudaMemcpyAsync(zk->d_ptau, sec[14].p, sec[14].size, cudaMemcpyHostToDevice, ctx->stream));
+
+    // additions: level-schedule.  level(i) = 1 + max(level of operands that are themselves additions)
+    const uint32_t n_w = zk->n_vars - zk->n_add;
+    const uint32_t na = zk->n_add;
+    std::vector<uint32_t> lvl(na), ia(na), ib(na);
+    uint32_t max_lvl = 0;
+    const uint8_t* ap = sec[3].p;
+    for (uint32_t i = 0; i < na; i++) {
+        memcpy(&ia[i], ap + (size_t)i * 72, 4);
+        memcpy(&ib[i], ap + (size_t)i * 72 + 4, 4);
+        uint32_t l = 0;
+        for (uint32_t s : {ia[i], ib[i]}) {
+            if (s >= n_w && s < zk->n_vars) {
+                const uint32_t j = s - n_w;
+                if (j >= i) {
+                    nzcb_zkey_free(zk);
+                    return ctx->fail(NZCB_E_INVALID, "zkey file: addition %u depends on a later addition", i);
+                }
+                l = std::max(l, lvl[j] + 1);
+            }
+        }
+        lvl[i] = l;
+        max_lvl = std::max(max_lvl, l);
+    }
+    std::vector<uint32_t> cnt(max_lvl + 2, 0);
+    for (uint32_t i = 0; i < na; i++) cnt[lvl[i] + 1]++;
+    for (uint32_t l = 0; l <= max_lvl; l++) cnt[l + 1] += cnt[l];
+    zk->level_off.assign(cnt.begin(), cnt.end());
+    if (na == 0) zk->level_off.assign(1, 0);
+    std::vector<uint32_t> pos(cnt.begin(), cnt.end() - 1), sa(na), sb(na), so(na);
+    std::vector<Fr> sac(na), sbc(na);
+    for (uint32_t i = 0; i < na; i++) {
+        const uint32_t d = pos[lvl[i]]++;
+        sa[d] = ia[i];
+        sb[d] = ib[i];
+        so[d] = i;
+        memcpy(sac[d].v, ap + (size_t)i * 72 + 8, 32);
+        memcpy(sbc[d].v, ap + (size_t)i * 72 + 40, 32);
+    }
+    const size_t na1 = std::max<uint32_t>(na, 1);
+    ZK_CUDA(cudaMalloc(&zk->d_add_a, na1 * 4));
+    ZK_CUDA(cudaMalloc(&zk->d_add_b, na1 * 4));
+    ZK_CUDA(cudaMalloc(&zk->d_add_out, na1 * 4));
+    ZK_CUDA(cudaMalloc(&zk->d_add_ac, na1 * 32));
+    ZK_CUDA(cudaMalloc(&zk->d_add_bc, na1 * 32));
+    if (na) {
+        ZK_CUDA(cudaMemcpyAsync(zk->d_add_a, sa.data(), (size_t)na * 4, cudaMemcpyHostToDevice, ctx->stream));
+        ZK_CUDA(cudaMemcpyAsync(zk->d_add_b, sb.data(), (size_t)na * 4, cudaMemcpyHostToDevice, ctx->stream));
+        ZK_CUDA(cudaMemcpyAsync(zk->d_add_out, so.data(), (size_t)na * 4, cudaMemcpyHostToDevice, ctx->stream));
+        ZK_CUDA(cudaMemcpyAsync(zk->d_add_ac, sac.data(), (size_t)na * 32, cudaMemcpyHostToDevice, ctx->stream));
+        ZK_CUDA(cudaMemcpyAsync(zk->d_add_bc, sbc.data(), (size_t)na * 32, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    ZK_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out = zk;
+    return 0;
+}
+
+// ------------------------------------------------------------------ prove
+namespace {
+
+struct Bufs {
+    Fr *w_le, *W, *A, *B, *C, *pol_a, *pol_b, *pol_c, *pol_z, *A4, *B4, *C4, *Z4, *num, *den, *T, *Tz, *pol_r, *pol_wxi,
+        *quot, *vals, *pub;
+    G1XYZZ* pts;
+    int* flags;
+};
+
+#define GETBUF(field, name, count)                                                            \
+    do {                                                                                      \
+        b.field = (decltype(b.field))ctx->scratch_get(name, (size_t)(count) * sizeof(*b.field)); \
+        if (!b.field) return ctx->fail(NZCB_E_NOMEM, "prove: cannot allocate " name);         \
+    } while (0)
+
+int get_bufs(nzcb_ctx* ctx, const nzcb_zkey* zk, Bufs& b) {
+    const size_t n = zk->n;
+    GETBUF(w_le, "pv_w_le", zk->n_vars);
+    GETBUF(W, "pv_W", zk->n_vars + 1);
+    GETBUF(A, "pv_A", n);
+    GETBUF(B, "pv_B", n);
+    GETBUF(C, "pv_C", n);
+    GETBUF(pol_a, "pv_pol_a", n + 8);
+    GETBUF(pol_b, "pv_pol_b", n + 8);
+    GETBUF(pol_c, "pv_pol_c", n + 8);
+    GETBUF(pol_z, "pv_pol_z", n + 8);
+    GETBUF(A4, "pv_A4", 4 * n);
+    GETBUF(B4, "pv_B4", 4 * n);
+    GETBUF(C4, "pv_C4", 4 * n);
+    GETBUF(Z4, "pv_Z4", 4 * n);
+    GETBUF(num, "pv_num", n);
+    GETBUF(den, "pv_den", n);
+    GETBUF(T, "pv_T", 4 * n);
+    GETBUF(Tz, "pv_Tz", 4 * n);
+    GETBUF(pol_r, "pv_pol_r", n + 8);
+    GETBUF(pol_wxi, "pv_pol_wxi", n + 8);
+    GETBUF(quot, "pv_quot", n + 8);
+    GETBUF(vals, "pv_vals", 16);
+    GETBUF(pub, "pv_pub", zk->n_public + 1);
+    GETBUF(pts, "pv_pts", 4);
+    GETBUF(flags, "pv_flags", 4);
+    return 0;
+}
+
+// evaluations -> (blinded coefficient polynomial, unblinded 4n evaluations)   [snarkjs to4T]
+int to4t(nzcb_ctx* ctx, const nzcb_zkey* zk, const Fr* d_evals, Fr* d_pol, Fr* d_ext, const Fr* pz, int k) {
+    const size_t n = zk->n;
+    NZ_CUDA(ctx, cudaMemcpyAsync(d_pol, d_evals, n * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->stream));
+    NZ_TRY(ntt_dev(ctx, d_pol, zk->power, true));
+    NZ_LAUNCH(ctx, k_copy_pad, div_up(4 * n, 256), 256, 0, d_pol, n, d_ext, 4 * n);
+    NZ_TRY(ntt_dev(ctx, d_ext, zk->power + 2, false));
+    Blind bl;
+    bl.k = k;
+    for (int i = 0; i < 3; i++) bl.pz[i] = i < k ? pz[i] : Fr::zero();
+    NZ_LAUNCH(ctx, k_blind, 1, 32, 0, d_pol, n, bl);
+    return 0;
+}
+
+int prove_one(nzcb_ctx* ctx, const nzcb_zkey* zk, const uint8_t* wtns, size_t wtns_len, const uint8_t* blinders_le,
+              nzcb_proof* out, uint8_t* public_le) {
+    NZ_CUDA(ctx, cudaSetDevice(ctx->device));
+    // ---- step 0: parse + check the witness file
+    std::map<uint32_t, Section> ws;
+    NZ_TRY(parse_binfile(ctx, wtns, wtns_len, "wtns", ws));
+    if (!ws.count(1) || !ws.count(2) || ws[1].size < 40) return ctx->fail(NZCB_E_INVALID, "wtns file: missing sections");
+    uint32_t n8, n_wit;
+    memcpy(&n8, ws[1].p, 4);
+    memcpy(&n_wit, ws[1].p + 36, 4);
+    if (n8 != 32 || memcmp(ws[1].p + 4, R_LE, 32) != 0)
+        return ctx->fail(NZCB_E_WITNESS, "Curve of the witness does not match the curve of the proving key");
+    const uint32_t n_w = zk->n_vars - zk->n_add;
+    if (n_wit != n_w || ws[2].size != (uint64_t)n_wit * 32)
+        return ctx->fail(NZCB_E_WITNESS, "Invalid witness length. Circuit: %u, witness: %u, %u", zk->n_vars, n_wit,
+                         zk->n_add);
+    const uint8_t* wv = ws[2].p;
+    const uint32_t n = zk->n, n_pub = zk->n_public;
+    if (n_pub + 1 > n_w) return ctx->fail(NZCB_E_WITNESS, "Invalid witness length: fewer values than public signals");
+
+    // blinders b1..b9 (Montgomery); index 0 unused
+    Fr bl[10];
+    bl[0] = Fr::zero();
+    for (int i = 1; i <= 9; i++) {
+        Fr v;
+        if (blinders_le) {
+            v = fr_from_le(blinders_le + (i - 1) * 32);
+            if (!fr_is_canonical(v)) return ctx->fail(NZCB_E_INVALID, "blinder b%d is not a canonical Fr element", i);
+        } else {
+            FILE* f = fopen("/dev/urandom", "rb");
+            if (!f) return ctx->fail(NZCB_E_INVALID, "cannot open the OS CSPRNG");
+            do {
+                if (fread(v.v, 1, 32, f) != 32) {
+                    fclose(f);
+                    return ctx->fail(NZCB_E_INVALID, "cannot read the OS CSPRNG");
+                }
+                v.v[7] &= 0x3fffffffu;
+            } while (!fr_is_canonical(v));
+            fclose(f);
+        }
+        bl[i] = v.to_mont();
+    }
+
+    Bufs b;
+    NZ_TRY(get_bufs(ctx, zk, b));
+    NZ_CUDA(ctx, cudaMemsetAsync(b.flags, 0, 4 * sizeof(int), ctx->stream));
+    NZ_CUDA(ctx, cudaMemcpyAsync(b.w_le, wv, (size_t)n_w * 32, cudaMemcpyHostToDevice, ctx->stream));
+    NZ_LAUNCH(ctx, k_wtns_to_mont, div_up(n_w, 256), 256, 0, b.w_le, b.W, (size_t)n_w);
+    for (size_t l = 0; l + 1 < zk->level_off.size(); l++) {
+        const uint32_t lo = zk->level_off[l], hi = zk->level_off[l + 1];
+        if (hi > lo)
+            NZ_LAUNCH(ctx, k_additions, div_up(hi - lo, 256), 256, 0, zk->d_add_a, zk->d_add_b, zk->d_add_ac,
+                      zk->d_add_bc, zk->d_add_out, lo, hi, zk->n_vars, n_w, b.W);
+    }
+    // ---- round 1
+    NZ_LAUNCH(ctx, k_gather, div_up(n, 256), 256, 0, zk->d_map[0], b.W, zk->n_vars, zk->n_cons, n, b.A);
+    NZ_LAUNCH(ctx, k_gather, div_up(n, 256), 256, 0, zk->d_map[1], b.W, zk->n_vars, zk->n_cons, n, b.B);
+    NZ_LAUNCH(ctx, k_gather, div_up(n, 256), 256, 0, zk->d_map[2], b.W, zk->n_vars, zk->n_cons, n, b.C);
+    {
+        const Fr pa[2] = {bl[2], bl[1]}, pb[2] = {bl[4], bl[3]}, pc[2] = {bl[6], bl[5]};
+        NZ_TRY(to4t(ctx, zk, b.A, b.pol_a, b.A4, pa, 2));
+        NZ_TRY(to4t(ctx, zk, b.B, b.pol_b, b.B4, pb, 2));
+        NZ_TRY(to4t(ctx, zk, b.C, b.pol_c, b.C4, pc, 2));
+    }
+    G1Affine cA, cB, cC, cZ, cT1, cT2, cT3, cWxi, cWxiw;
+    NZ_TRY(msm_dev(ctx, zk->d_ptau, (const uint32_t*)b.pol_a, (size_t)n + 2, true, b.pts + 0));
+    NZ_TRY(msm_to_host_affine(ctx, b.pts + 0, &cA));
+    NZ_TRY(msm_dev(ctx, zk->d_ptau, (const uint32_t*)b.pol_b, (size_t)n + 2, true, b.pts + 1));
+    NZ_TRY(msm_to_host_affine(ctx, b.pts + 1, &cB));
+    NZ_TRY(msm_dev(ctx, zk->d_ptau, (const uint32_t*)b.pol_c, (size_t)n + 2, true, b.pts + 2));
+    NZ_TRY(msm_to_host_affine(ctx, b.pts + 2, &cC));
+    g1_to_be(cA, out->A);
+    g1_to_be(cB, out->B);
+    g1_to_be(cC, out->C);
+
+    // ---- round 2
+    std::vector<uint8_t> tr;
+    std::vector<Fr> pub_m(n_pub + 1);
+    for (uint32_t i = 0; i < n_pub; i++) {
+        const Fr v = fr_from_le(wv + (size_t)(i + 1) * 32);  // A[i] = w[i+1] for the public-input gates
+        if (!fr_is_canonical(v)) return ctx->fail(NZCB_E_WITNESS, "witness value %u is not reduced", i + 1);
+        pub_m[i] = v.to_mont();
+        uint8_t be[32];
+        to_be_bytes(pub_m[i], be);
+        append(tr, be, 32);
+        if (public_le) memcpy(public_le + (size_t)i * 32, wv + (size_t)(i + 1) * 32, 32);
+    }
+    append(tr, out->A, 64);
+    append(tr, out->B, 64);
+    append(tr, out->C, 64);
+    const Fr beta = hash_to_fr(tr);
+    uint8_t be32[32];
+    to_be_bytes(beta, be32);
+    const Fr gamma = hash_to_fr(std::vector<uint8_t>(be32, be32 + 32));
+
+    const Fr *Wn = nullptr, *W4n = nullptr;
+    NZ_TRY(get_twiddles_pub(ctx, zk->power, false, &Wn));
+    NZ_TRY(get_twiddles_pub(ctx, zk->power + 2, false, &W4n));
+    const size_t N = n;
+    const Fr* S1 = zk->d_sigma;
+    const Fr* S14 = zk->d_sigma + N;
+    const Fr* S2 = zk->d_sigma + 5 * N;
+    const Fr* S24 = zk->d_sigma + 6 * N;
+    const Fr* S3 = zk->d_sigma + 10 * N;
+    const Fr* S34 = zk->d_sigma + 11 * N;
+    {
+        R2Args a;
+        a.A = b.A; a.B = b.B; a.C = b.C;
+        a.S14 = S14; a.S24 = S24; a.S34 = S34; a.Wn = Wn;
+        a.beta = beta; a.gamma = gamma; a.k1 = zk->k1; a.k2 = zk->k2;
+        a.n = n; a.power = zk->power; a.num = b.num; a.den = b.den;
+        NZ_LAUNCH(ctx, k_round2_terms, div_up(n, 128), 128, 0, a);
+    }
+    NZ_TRY(batch_inverse(ctx, b.den, n));
+    NZ_LAUNCH(ctx, k_mul_inplace, div_up(n, 256), 256, 0, b.num, b.den, (size_t)n);
+    // Z[i] = prod_{j<i} num_j/den_j ; the wrap-around product must be 1
+    NZ_TRY(prefix_product(ctx, b.num, n, b.den, b.vals + 0));
+    {
+        Fr total;
+        NZ_CUDA(ctx, cudaMemcpyAsync(&total, b.vals + 0, sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+        NZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (total != Fr::one()) return ctx->fail(NZCB_E_COPY, "Copy constraints does not match");
+    }
+    {
+        const Fr pz[3] = {bl[9], bl[8], bl[7]};
+        NZ_TRY(to4t(ctx, zk, b.den, b.pol_z, b.Z4, pz, 3));
+    }
+    NZ_TRY(msm_dev(ctx, zk->d_ptau, (const uint32_t*)b.pol_z, (size_t)n + 3, true, b.pts + 0));
+    NZ_TRY(msm_to_host_affine(ctx, b.pts + 0, &cZ));
+    g1_to_be(cZ, out->Z);
+
+    // ---- round 3
+    const Fr alpha = hash_to_fr(std::vector<uint8_t>(out->Z, out->Z + 64));
+    const Fr alpha2 = alpha * alpha;
+    NZ_CUDA(ctx, cudaMemcpyAsync(b.pub, pub_m.data(), (size_t)(n_pub + 1) * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    {
+        R3Args g;
+        g.A4 = b.A4; g.B4 = b.B4; g.C4 = b.C4; g.Z4 = b.Z4;
+        g.QM4 = zk->d_q[0] + N; g.QL4 = zk->d_q[1] + N; g.QR4 = zk->d_q[2] + N; g.QO4 = zk->d_q[3] + N; g.QC4 = zk->d_q[4] + N;
+        g.S14 = S14; g.S24 = S24; g.S34 = S34; g.L4 = zk->d_lag; g.pub = b.pub; g.W4n = W4n;
+        for (int i = 0; i < 10; i++) g.b[i] = bl[i];
+        g.beta = beta; g.gamma = gamma; g.alpha = alpha; g.alpha2 = alpha2; g.k1 = zk->k1; g.k2 = zk->k2;
+        g.wn = fr_root_host(zk->power);
+        const Fr w4 = fr_root_host(2), one = Fr::one(), two = one + one, four = two + two, eight = four + four;
+        const Fr zero = Fr::zero();
+        g.Z1[0] = zero; g.Z1[1] = w4 - one; g.Z1[2] = zero - two; g.Z1[3] = zero - one - w4;
+        g.Z2[0] = zero; g.Z2[1] = zero - two * w4; g.Z2[2] = four; g.Z2[3] = two * w4;
+        g.Z3[0] = zero; g.Z3[1] = two + two * w4; g.Z3[2] = zero - eight; g.Z3[3] = two - two * w4;
+        g.n = n; g.power = zk->power; g.n_pub = n_pub; g.T = b.T; g.Tz = b.Tz;
+        NZ_LAUNCH(ctx, k_round3, div_up(4 * N, 128), 128, 0, g);
+    }
+    NZ_TRY(ntt_dev(ctx, b.T, zk->power + 2, true));
+    NZ_LAUNCH(ctx, k_div_zh, div_up(n, 256), 256, 0, b.T, n, b.flags);
+    NZ_TRY(ntt_dev(ctx, b.Tz, zk->power + 2, true));
+    NZ_LAUNCH(ctx, k_add_tz, div_up(4 * N, 256), 256, 0, b.T, b.Tz, n, b.flags);
+    {
+        int fl[4];
+        NZ_CUDA(ctx, cudaMemcpyAsync(fl, b.flags, sizeof(fl), cudaMemcpyDeviceToHost, ctx->stream));
+        NZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (fl[0]) return ctx->fail(NZCB_E_DIVIDE, "T Polynomial is not divisible");
+        if (fl[1]) return ctx->fail(NZCB_E_DIVIDE, "Tz Polynomial is not well calculated");
+    }
+    Fr* pol_t = b.T;  // 3n + 6 coefficients
+    NZ_TRY(msm_dev(ctx, zk->d_ptau, (const uint32_t*)pol_t, N, true, b.pts + 0));
+    NZ_TRY(msm_to_host_affine(ctx, b.pts + 0, &cT1));
+    NZ_TRY(msm_dev(ctx, zk->d_ptau, (const uint32_t*)(pol_t + N), N, true, b.pts + 1));
+    NZ_TRY(msm_to_host_affine(ctx, b.pts + 1, &cT2));
+    NZ_TRY(msm_dev(ctx, zk->d_ptau, (const uint32_t*)(pol_t + 2 * N), N + 6, true, b.pts + 2));
+    NZ_TRY(msm_to_host_affine(ctx, b.pts + 2, &cT3));
+    g1_to_be(cT1, out->T1);
+    g1_to_be(cT2, out->T2);
+    g1_to_be(cT3, out->T3);
+
+    // ---- round 4
+    tr.clear();
+    append(tr, out->T1, 64);
+    append(tr, out->T2, 64);
+    append(tr, out->T3, 64);
+    const Fr xi = hash_to_fr(tr);
+    const Fr wn = fr_root_host(zk->power);
+    const Fr xiw = xi * wn;
+    // vals: 1 eval_a, 2 eval_b, 3 eval_c, 4 eval_s1, 5 eval_s2, 6 eval_t, 7 eval_zw, 8 eval_r, 9/10 remainders
+    NZ_TRY(poly_horner(ctx, b.pol_a, N + 2, xi, b.vals + 1, nullptr));
+    NZ_TRY(poly_horner(ctx, b.pol_b, N + 2, xi, b.vals + 2, nullptr));
+    NZ_TRY(poly_horner(ctx, b.pol_c, N + 2, xi, b.vals + 3, nullptr));
+    NZ_TRY(poly_horner(ctx, S1, N, xi, b.vals + 4, nullptr));
+    NZ_TRY(poly_horner(ctx, S2, N, xi, b.vals + 5, nullptr));
+    NZ_TRY(poly_horner(ctx, pol_t, 3 * N + 6, xi, b.vals + 6, nullptr));
+    NZ_TRY(poly_horner(ctx, b.pol_z, N + 3, xiw, b.vals + 7, nullptr));
+    Fr ev[16];
+    NZ_CUDA(ctx, cudaMemcpyAsync(ev, b.vals, 8 * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+    NZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const Fr ea = ev[1], eb = ev[2], ec = ev[3], es1 = ev[4], es2 = ev[5], et = ev[6], ezw = ev[7];
+    const Fr coef_ab = ea * eb;
+    const Fr bxi = beta * xi;
+    const Fr e2 = (ea + bxi + gamma) * (eb + bxi * zk->k1 + gamma) * (ec + bxi * zk->k2 + gamma) * alpha;
+    const Fr e3 = (ea + beta * es1 + gamma) * (eb + beta * es2 + gamma) * beta * ezw * alpha;
+    Fr xim = xi;
+    for (uint32_t i = 0; i < zk->power; i++) xim = xim.sqr();
+    const Fr eval_l1 = (xim - Fr::one()) * ((xi - Fr::one()) * Fr::from_u64(n)).inv();
+    const Fr e4 = eval_l1 * alpha2;
+    {
+        R4Args g;
+        g.pol_z = b.pol_z; g.qm = zk->d_q[0]; g.ql = zk->d_q[1]; g.qr = zk->d_q[2]; g.qo = zk->d_q[3]; g.qc = zk->d_q[4];
+        g.s3 = S3; g.coefz = e2 + e4; g.coef_ab = coef_ab; g.ea = ea; g.eb = eb; g.ec = ec; g.e3 = e3;
+        g.n = n; g.pol_r = b.pol_r;
+        NZ_LAUNCH(ctx, k_pol_r, div_up(n + 3, 256), 256, 0, g);
+    }
+    NZ_TRY(poly_horner(ctx, b.pol_r, N + 3, xi, b.vals + 8, nullptr));
+    Fr er;
+    NZ_CUDA(ctx, cudaMemcpyAsync(&er, b.vals + 8, sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+    NZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    to_be_bytes(ea, out->eval_a);
+    to_be_bytes(eb, out->eval_b);
+    to_be_bytes(ec, out->eval_c);
+    to_be_bytes(es1, out->eval_s1);
+    to_be_bytes(es2, out->eval_s2);
+    to_be_bytes(ezw, out->eval_zw);
+    to_be_bytes(er, out->eval_r);
+
+    // ---- round 5
+    tr.clear();
+    append(tr, out->eval_a, 32);
+    append(tr, out->eval_b, 32);
+    append(tr, out->eval_c, 32);
+    append(tr, out->eval_s1, 32);
+    append(tr, out->eval_s2, 32);
+    append(tr, out->eval_zw, 32);
+    append(tr, out->eval_r, 32);
+    Fr v[7];
+    v[0] = Fr::one();
+    v[1] = hash_to_fr(tr);
+    for (int i = 2; i <= 6; i++) v[i] = v[i - 1] * v[1];
+    {
+        R5Args g;
+        g.pol_t = pol_t; g.pol_r = b.pol_r; g.pol_a = b.pol_a; g.pol_b = b.pol_b; g.pol_c = b.pol_c; g.s1 = S1; g.s2 = S2;
+        g.xim = xim; g.xi2m = xim * xim;
+        for (int i = 0; i < 7; i++) g.v[i] = v[i];
+        g.w0_sub = et + v[1] * er + v[2] * ea + v[3] * eb + v[4] * ec + v[5] * es1 + v[6] * es2;
+        g.n = n; g.out = b.pol_wxi;
+        NZ_LAUNCH(ctx, k_pol_wxi, div_up(n + 6, 256), 256, 0, g);
+    }
+    NZ_TRY(poly_horner(ctx, b.pol_wxi, N + 6, xi, b.vals + 9, b.quot));
+    NZ_TRY(msm_dev(ctx, zk->d_ptau, (const uint32_t*)b.quot, N + 6, true, b.pts + 0));
+    NZ_TRY(msm_to_host_affine(ctx, b.pts + 0, &cWxi));
+    // W_{xi w} = (pol_z - eval_zw) / (X - xi w)
+    NZ_CUDA(ctx, cudaMemcpyAsync(b.pol_wxi, b.pol_z, (N + 3) * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->stream));
+    NZ_LAUNCH(ctx, k_sub_at0, 1, 1, 0, b.pol_wxi, ezw);
+    NZ_TRY(poly_horner(ctx, b.pol_wxi, N + 3, xiw, b.vals + 10, b.quot));
+    NZ_TRY(msm_dev(ctx, zk->d_ptau, (const uint32_t*)b.quot, N + 3, true, b.pts + 1));
+    NZ_TRY(msm_to_host_affine(ctx, b.pts + 1, &cWxiw));
+    Fr rem[2];
+    NZ_CUDA(ctx, cudaMemcpyAsync(rem, b.vals + 9, 2 * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+    NZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (!rem[0].is_zero() || !rem[1].is_zero()) return ctx->fail(NZCB_E_DIVIDE, "Polinomial does not divide");
+    g1_to_be(cWxi, out->Wxi);
+    g1_to_be(cWxiw, out->Wxiw);
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int32_t nzcb_plonk_prove(nzcb_ctx* ctx, const nzcb_zkey* zk, const uint8_t* wtns, size_t wtns_len,
+                                    const uint8_t* blinders_le, nzcb_proof* out, uint8_t* public_le) {
+    if (!ctx || !zk || !wtns || !out) return NZCB_E_INVALID;
+    if (zk->ctx != ctx) return ctx->fail(NZCB_E_INVALID, "zkey was loaded on a different context");
+    cudaEventRecord(ctx->ev0, ctx->stream);
+    const int rc = prove_one(ctx, zk, wtns, wtns_len, blinders_le, out, public_le);
+    if (rc != 0) {
+        cudaStreamSynchronize(ctx->stream);
+        return rc;
+    }
+    cudaEventRecord(ctx->ev1, ctx->stream);
+    NZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1);
+    return 0;
+}
+
+extern "C" int32_t nzcb_plonk_prove_batch(nzcb_ctx* ctx, const nzcb_zkey* zk, const uint8_t* const* wtns,
+                                          const size_t* wtns_len, const uint8_t* blinders_le, size_t B, nzcb_proof* out,
+                                          uint8_t* public_le, int32_t* status) {
+    if (!ctx || !zk || !wtns || !wtns_len || !out) return NZCB_E_INVALID;
+    if (zk->ctx != ctx) return ctx->fail(NZCB_E_INVALID, "zkey was loaded on a different context");
+    cudaEventRecord(ctx->ev0, ctx->stream);
+    int32_t first_err = 0;
+    for (size_t i = 0; i < B; i++) {
+        const int rc = prove_one(ctx, zk, wtns[i], wtns_len[i], blinders_le ? blinders_le + i * 9 * 32 : nullptr, out + i,
+                                 public_le ? public_le + i * (size_t)zk->n_public * 32 : nullptr);
+        if (status) status[i] = rc;
+        if (rc != 0) {
+            cudaStreamSynchronize(ctx->stream);
+            if (rc == NZCB_E_CUDA || rc == NZCB_E_NOMEM) return rc;  // the device is gone: stop
+            if (!first_err) first_err = rc;
+            memset(out + i, 0, sizeof(nzcb_proof));
+        }
+    }
+    cudaEventRecord(ctx->ev1, ctx->stream);
+    NZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1);
+    return status ? 0 : first_err;
+}
+
+// ------------------------------------------------------------------ proof.json
+namespace {
+// 256-bit big-endian bytes -> decimal string
+std::string be_to_dec(const uint8_t* be, size_t len) {
+    std::vector<uint32_t> limbs((len + 3) / 4, 0);  // little-endian base 2^32
+    for (size_t i = 0; i < len; i++) limbs[(len - 1 - i) / 4] |= (uint32_t)be[i] << (8 * ((len - 1 - i) % 4));
+    std::string s;
+    bool nonzero = true;
+    while (nonzero) {
+        uint64_t rem = 0;
+        nonzero = false;
+        for (size_t k = limbs.size(); k-- > 0;) {
+            const uint64_t cur = (rem << 32) | limbs[k];
+            limbs[k] = (uint32_t)(cur / 1000000000u);
+            rem = cur % 1000000000u;
+            if (limbs[k]) nonzero = true;
+        }
+        char buf[16];
+        snprintf(buf, sizeof(buf), nonzero ? "%09u" : "%u", (unsigned)rem);
+        s = std::string(buf) + s;
+    }
+    return s;
+}
+void json_point(std::string& o, const char* key, const uint8_t p[64]) {
+    bool inf = true;
+    for (int i = 0; i < 64; i++) inf = inf && p[i] == 0;
+    o += " \"";
+    o += key;
+    o += "\": [\n  \"";
+    o += inf ? "0" : be_to_dec(p, 32);
+    o += "\",\n  \"";
+    o += inf ? "1" : be_to_dec(p + 32, 32);
+    o += "\",\n  \"";
+    o += inf ? "0" : "1";
+    o += "\"\n ],\n";
+}
+void json_scalar(std::string& o, const char* key, const uint8_t p[32]) {
+    o += " \"";
+    o += key;
+    o += "\": \"";
+    o += be_to_dec(p, 32);
+    o += "\",\n";
+}
+}  // namespace
+
+extern "C" int32_t nzcb_proof_to_json(const nzcb_proof* p, char* buf, size_t* len) {
+    if (!p || !len) return NZCB_E_INVALID;
+    std::string o = "{\n";
+    json_point(o, "A", p->A);
+    json_point(o, "B", p->B);
+    json_point(o, "C", p->C);
+    json_point(o, "Z", p->Z);
+    json_point(o, "T1", p->T1);
+    json_point(o, "T2", p->T2);
+    json_point(o, "T3", p->T3);
+    json_scalar(o, "eval_a", p->eval_a);
+    json_scalar(o, "eval_b", p->eval_b);
+    json_scalar(o, "eval_c", p->eval_c);
+    json_scalar(o, "eval_s1", p->eval_s1);
+    json_scalar(o, "eval_s2", p->eval_s2);
+    json_scalar(o, "eval_zw", p->eval_zw);
+    json_scalar(o, "eval_r", p->eval_r);
+    json_point(o, "Wxi", p->Wxi);
+    json_point(o, "Wxiw", p->Wxiw);
+    o += " \"protocol\": \"plonk\",\n \"curve\": \"bn128\"\n}";
+    const size_t need = o.size() + 1;
+    if (!buf || *len < need) {
+        *len = need;
+        return buf ? NZCB_E_INVALID : 0;
+    }
+    memcpy(buf, o.c_str(), need);
+    *len = need;
+    return 0;
+}

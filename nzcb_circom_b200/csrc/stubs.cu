@@ -4,12 +4,6 @@
 extern "C" {
 int32_t nzcb_srs_g1(nzcb_ctx* ctx, const uint8_t*, size_t, uint8_t*) { NZ_STUB(ctx, "nzcb_srs_g1"); }
 int32_t nzcb_plonk_setup(nzcb_ctx* ctx, const uint8_t*, size_t, const uint8_t*, size_t, const uint8_t*, uint8_t*, size_t*) { NZ_STUB(ctx, "nzcb_plonk_setup"); }
-int32_t nzcb_zkey_load(nzcb_ctx* ctx, const uint8_t*, size_t, nzcb_zkey**) { NZ_STUB(ctx, "nzcb_zkey_load"); }
-void nzcb_zkey_free(nzcb_zkey*) {}
-int32_t nzcb_zkey_info(const nzcb_zkey*, uint32_t*, uint32_t*, uint32_t*, uint32_t*, uint32_t*) { return NZCB_E_INVALID; }
-int32_t nzcb_plonk_prove(nzcb_ctx* ctx, const nzcb_zkey*, const uint8_t*, size_t, const uint8_t*, nzcb_proof*, uint8_t*) { NZ_STUB(ctx, "nzcb_plonk_prove"); }
-int32_t nzcb_plonk_prove_batch(nzcb_ctx* ctx, const nzcb_zkey*, const uint8_t* const*, const size_t*, const uint8_t*, size_t, nzcb_proof*, uint8_t*, int32_t*) { NZ_STUB(ctx, "nzcb_plonk_prove_batch"); }
-int32_t nzcb_proof_to_json(const nzcb_proof*, char*, size_t*) { return NZCB_E_INVALID; }
 int32_t nzcb_circuit_load(nzcb_ctx* ctx, const uint8_t*, size_t, nzcb_circuit**) { NZ_STUB(ctx, "nzcb_circuit_load"); }
 void nzcb_circuit_free(nzcb_circuit*) {}
 int32_t nzcb_circuit_info(const nzcb_circuit*, uint32_t*, uint32_t*, uint32_t*) { return NZCB_E_INVALID; }

@@ -1,0 +1,219 @@
+"""Host mirror of the snarkjs 0.4.12 entry points on the proving path
+(un-vendored npm dependency, /root/reference/yarn.lock:7279; the reference's
+own use is the Makefile recipe /root/reference/Makefile:54-62 and the
+``wasm_tester`` call sites of test/nzcp.js).  Same names and argument meaning
+as the JS:
+
+    plonk.setup(r1cs, ptau)            -> zkey bytes        (`snarkjs plonk setup`)
+    plonk.prove(zkey, wtns)            -> (proof, publicSignals)
+    plonk.fullProve(input, circuit, zkey)
+    wtns.calculate(input, circuit)     -> .wtns bytes
+
+``zkey`` / ``wtns`` are the file *bytes* ({type:"mem"} in JS) or a path;
+``proof`` is the dict snarkjs returns (decimal strings).  Everything below the
+C ABI runs on the GPU in libnzcb.so; errors surface as NzcbError carrying
+snarkjs' message.  Deterministic proofs: pass ``blinders`` (nine ints, the
+values ``Fr.random()`` would have returned in round 1, b1..b9).
+"""
+import ctypes
+import json
+import struct
+
+from ._lib import NzcbError, Proof, default_context
+
+R_MOD = 0x30644e72e131a029b85045b68181585d2833e84879b9709143e1f593f0000001
+
+_POINTS = ("A", "B", "C", "Z", "T1", "T2", "T3", "Wxi", "Wxiw")
+_EVALS = ("eval_a", "eval_b", "eval_c", "eval_s1", "eval_s2", "eval_zw", "eval_r")
+
+
+def _bytes_of(x):
+    if isinstance(x, (bytes, bytearray, memoryview)):
+        return bytes(x)
+    with open(x, "rb") as f:
+        return f.read()
+
+
+class ZKey:
+    """A PLONK proving key made device resident once per process (nzcb_zkey_load)."""
+
+    def __init__(self, zkey, ctx=None):
+        self.ctx = ctx or default_context()
+        data = _bytes_of(zkey)
+        h = ctypes.c_void_p()
+        buf = (ctypes.c_uint8 * len(data)).from_buffer_copy(data)
+        self.ctx.check(self.ctx.lib.nzcb_zkey_load(self.ctx.h, buf, len(data), ctypes.byref(h)))
+        self.h = h
+        vals = [ctypes.c_uint32() for _ in range(5)]
+        self.ctx.lib.nzcb_zkey_info(self.h, *[ctypes.byref(v) for v in vals])
+        self.n_vars, self.n_public, self.domain_size, self.n_additions, self.n_constraints = (v.value for v in vals)
+
+    def close(self):
+        if getattr(self, "h", None) and self.ctx.h:
+            self.ctx.lib.nzcb_zkey_free(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_zkey_cache = {}
+
+
+def _as_zkey(zkey, ctx):
+    if isinstance(zkey, ZKey):
+        return zkey
+    if isinstance(zkey, str):  # path: cache like a long-lived prover process would
+        key = (zkey, id(ctx))
+        if key not in _zkey_cache:
+            _zkey_cache[key] = ZKey(zkey, ctx)
+        return _zkey_cache[key]
+    return ZKey(zkey, ctx)
+
+
+def proof_struct_to_obj(ps: Proof):
+    """nzcb_proof -> the object snarkjs returns from plonk.prove (decimal strings)."""
+    obj = {}
+
+    def pt(raw):
+        raw = bytes(raw)
+        if raw == bytes(64):
+            return ["0", "1", "0"]
+        return [str(int.from_bytes(raw[:32], "big")), str(int.from_bytes(raw[32:], "big")), "1"]
+
+    for k in ("A", "B", "C", "Z", "T1", "T2", "T3"):
+        obj[k] = pt(getattr(ps, k))
+    for k in _EVALS:
+        obj[k] = str(int.from_bytes(bytes(getattr(ps, k)), "big"))
+    obj["Wxi"] = pt(ps.Wxi)
+    obj["Wxiw"] = pt(ps.Wxiw)
+    obj["protocol"] = "plonk"
+    obj["curve"] = "bn128"
+    return obj
+
+
+def _blinder_buf(blinders):
+    if blinders is None:
+        return None
+    if len(blinders) != 9:
+        raise ValueError("blinders must be the nine values b1..b9")
+    raw = b"".join(int(x).to_bytes(32, "little") for x in blinders)
+    return (ctypes.c_uint8 * len(raw)).from_buffer_copy(raw)
+
+
+class _Plonk:
+    def prove(self, zkey, wtns, blinders=None, ctx=None, raw=False):
+        """snarkjs.plonk.prove(zkeyFile, wtnsFile) -> (proof, publicSignals)."""
+        ctx = ctx or (zkey.ctx if isinstance(zkey, ZKey) else default_context())
+        zk = _as_zkey(zkey, ctx)
+        w = _bytes_of(wtns)
+        wbuf = (ctypes.c_uint8 * len(w)).from_buffer_copy(w)
+        ps = Proof()
+        pub = (ctypes.c_uint8 * (32 * max(1, zk.n_public)))()
+        ctx.check(ctx.lib.nzcb_plonk_prove(ctx.h, zk.h, wbuf, len(w), _blinder_buf(blinders), ctypes.byref(ps), pub))
+        public = [str(int.from_bytes(bytes(pub[i * 32:(i + 1) * 32]), "little")) for i in range(zk.n_public)]
+        if raw:
+            return bytes(ps), public
+        return proof_struct_to_obj(ps), public
+
+    def prove_batch(self, zkey, wtns_list, blinders_list=None, ctx=None):
+        """B independent proofs on this process's GPU; returns [(proof bytes | None, publicSignals, status)]."""
+        ctx = ctx or (zkey.ctx if isinstance(zkey, ZKey) else default_context())
+        zk = _as_zkey(zkey, ctx)
+        B = len(wtns_list)
+        bufs = [(ctypes.c_uint8 * len(w)).from_buffer_copy(w) for w in wtns_list]
+        ptrs = (ctypes.c_void_p * B)(*[ctypes.addressof(b) for b in bufs])
+        lens = (ctypes.c_size_t * B)(*[len(w) for w in wtns_list])
+        bl = None
+        if blinders_list is not None:
+            raw = b"".join(int(x).to_bytes(32, "little") for bs in blinders_list for x in bs)
+            bl = (ctypes.c_uint8 * len(raw)).from_buffer_copy(raw)
+        out = (Proof * B)()
+        pub = (ctypes.c_uint8 * (32 * max(1, zk.n_public) * B))()
+        status = (ctypes.c_int32 * B)()
+        ctx.check(ctx.lib.nzcb_plonk_prove_batch(ctx.h, zk.h, ptrs, lens, bl, B, out, pub, status))
+        res = []
+        for i in range(B):
+            pb = bytes(pub[i * 32 * zk.n_public:(i + 1) * 32 * zk.n_public])
+            public = [str(int.from_bytes(pb[k * 32:(k + 1) * 32], "little")) for k in range(zk.n_public)]
+            res.append((bytes(out[i]) if status[i] == 0 else None, public, int(status[i])))
+        return res
+
+    def proof_json(self, proof_bytes, ctx=None):
+        """proof.json text exactly as snarkjs writes it (JSON.stringify(proof, null, 1))."""
+        ctx = ctx or default_context()
+        ps = Proof.from_buffer_copy(proof_bytes)
+        n = ctypes.c_size_t(0)
+        ctx.lib.nzcb_proof_to_json(ctypes.byref(ps), None, ctypes.byref(n))
+        buf = ctypes.create_string_buffer(n.value)
+        rc = ctx.lib.nzcb_proof_to_json(ctypes.byref(ps), buf, ctypes.byref(n))
+        if rc != 0:
+            raise NzcbError(rc, "proof_to_json failed")
+        return buf.value.decode()
+
+    def setup(self, r1cs, srs_g1_lem, x2_g2_lem=bytes(128), ctx=None):
+        """`snarkjs plonk setup circuit.r1cs pot.ptau circuit.zkey` (the ptau reduced to its
+        tauG1 points, affine LEM, as section 2 of the .ptau holds them)."""
+        ctx = ctx or default_context()
+        r = _bytes_of(r1cs)
+        rbuf = (ctypes.c_uint8 * len(r)).from_buffer_copy(r)
+        sbuf = (ctypes.c_uint8 * len(srs_g1_lem)).from_buffer_copy(srs_g1_lem)
+        x2 = (ctypes.c_uint8 * 128).from_buffer_copy(x2_g2_lem)
+        n = ctypes.c_size_t(0)
+        ctx.check(ctx.lib.nzcb_plonk_setup(ctx.h, rbuf, len(r), sbuf, len(srs_g1_lem) // 64, x2, None, ctypes.byref(n)))
+        out = (ctypes.c_uint8 * n.value)()
+        ctx.check(ctx.lib.nzcb_plonk_setup(ctx.h, rbuf, len(r), sbuf, len(srs_g1_lem) // 64, x2, out, ctypes.byref(n)))
+        return bytes(out)
+
+    def fullProve(self, input, circuit, zkey, blinders=None, ctx=None):
+        """snarkjs.plonk.fullProve(input, wasmFile, zkeyFile): witness on the GPU, then prove."""
+        w = wtns.calculate(input, circuit, ctx=ctx)
+        return self.prove(zkey, w, blinders=blinders, ctx=ctx)
+
+
+class _Powersoftau:
+    def new_g1(self, tau, count, ctx=None):
+        """[tau^i]G1 for i < count as affine LEM bytes: the tauG1 section of an insecure,
+        known-trapdoor `snarkjs powersoftau new` (Makefile:64-67 role; synthetic inputs only)."""
+        ctx = ctx or default_context()
+        t = (ctypes.c_uint8 * 32).from_buffer_copy(int(tau % R_MOD).to_bytes(32, "little"))
+        out = (ctypes.c_uint8 * (64 * count))()
+        ctx.check(ctx.lib.nzcb_srs_g1(ctx.h, t, count, out))
+        return bytes(out)
+
+
+class _Wtns:
+    def calculate(self, input, circuit, ctx=None):
+        """snarkjs.wtns.calculate(input, wasmFile, {type:"mem"}) -> .wtns bytes.  `circuit` is a
+        compiled circuit (nzcb_circom_b200.circom_tester.WasmTester)."""
+        w = circuit.calculateWitness(input, True, ctx=ctx)
+        return write_wtns(w)
+
+
+def write_wtns(witness):
+    """.wtns v2: header section 1, values section 2, canonical LE."""
+    hdr = struct.pack("<I", 32) + R_MOD.to_bytes(32, "little") + struct.pack("<I", len(witness))
+    body = b"".join(int(x).to_bytes(32, "little") for x in witness)
+    out = b"wtns" + struct.pack("<II", 2, 2)
+    out += struct.pack("<IQ", 1, len(hdr)) + hdr
+    out += struct.pack("<IQ", 2, len(body)) + body
+    return out
+
+
+def wtns_from_raw(raw_le: bytes):
+    """wrap nWitness x 32 B canonical LE values (nzcb_witness_batch output) as a .wtns file"""
+    n = len(raw_le) // 32
+    hdr = struct.pack("<I", 32) + R_MOD.to_bytes(32, "little") + struct.pack("<I", n)
+    out = b"wtns" + struct.pack("<II", 2, 2)
+    out += struct.pack("<IQ", 1, len(hdr)) + hdr
+    out += struct.pack("<IQ", 2, len(raw_le)) + raw_le
+    return out
+
+
+plonk = _Plonk()
+powersoftau = _Powersoftau()
+wtns = _Wtns()
+__all__ = ["plonk", "powersoftau", "wtns", "ZKey", "write_wtns", "wtns_from_raw", "json"]

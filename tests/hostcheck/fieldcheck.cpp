@@ -43,3 +43,6 @@ int fc_g1_op(int op, const uint8_t* a, const uint8_t* b, uint64_t k, uint8_t* ou
     return 0;
 }
 }
+
+#include "../../nzcb_circom_b200/csrc/keccak.h"
+extern "C" void fc_keccak256(const uint8_t* data, size_t len, uint8_t* out) { nzcb::keccak256(data, len, out); }
