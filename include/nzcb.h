@@ -130,6 +130,13 @@ int32_t nzcb_circuit_info(const nzcb_circuit* c, uint32_t* n_witness, uint32_t* 
 int32_t nzcb_witness_batch(nzcb_ctx* ctx, const nzcb_circuit* c, const uint8_t* inputs_le, size_t B,
                            uint8_t* wtns_out, int32_t* status);
 
+/* snarkjs plonk.fullProve for B passes: witness program then prover, wires never leave HBM.
+ * status[i] = 0, NZCB_E_ASSERT (pass rejected by the circuit) or a prover error; a failed
+ * pass zeroes out[i] and never fails the batch. */
+int32_t nzcb_plonk_fullprove_batch(nzcb_ctx* ctx, const nzcb_circuit* c, const nzcb_zkey* zk, const uint8_t* inputs_le,
+                                   size_t B, const uint8_t* blinders_le /* B x 9 x 32 or NULL */, nzcb_proof* out,
+                                   uint8_t* public_le /* B x nPublic x 32 */, int32_t* status /* B */);
+
 #ifdef __cplusplus
 }
 #endif

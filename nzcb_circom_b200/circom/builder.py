@@ -1,0 +1,505 @@
+"""Circuit builder: the role `circom --r1cs --wasm --O2` plays for the reference
+(/root/reference/Makefile:5-15).  circom itself (a Rust binary) is absent from
+this image and so are the SHA gadgets it would compile, so
+the templates are restated on this small eDSL, which emits
+
+  * the R1CS (``.r1cs`` bytes) that `plonk setup` consumes, and
+  * a *witness program*: one instruction per wire (the straight-line program a
+    circom-generated WASM runs), level-scheduled so the GPU interpreter
+    (csrc/witness.cu) can run every level in parallel.
+
+Semantics follow circom: ``<==`` is "assign and constrain", ``<--`` is a hint
+(BITS / INV instructions), ``===`` adds a constraint plus a run-time assert.
+Like ``--O2`` the builder never materialises a signal that is a linear
+combination of others: linear expressions are carried symbolically (class LC)
+and only quadratic assignments, hints, inputs and outputs become wires.  Wire
+order is circom's convention where it is observable: 1, outputs, inputs in
+declaration order (test/nzcp.js:44, test/cbor.js:191-193), then internals.
+"""
+import struct
+
+R = 0x30644e72e131a029b85045b68181585d2833e84879b9709143e1f593f0000001
+
+OP_LIN, OP_MUL, OP_BITS, OP_INV, OP_ASSERT = 1, 2, 3, 4, 5
+
+
+class LC:
+    """Linear combination  k + sum coef * wire.  Immutable by convention."""
+    __slots__ = ("t", "k")
+
+    def __init__(self, t=None, k=0):
+        self.t = t if t is not None else {}
+        self.k = k % R
+
+    @staticmethod
+    def of(x):
+        if isinstance(x, LC):
+            return x
+        if isinstance(x, int):
+            return LC(None, x)
+        raise TypeError(f"cannot use {type(x)} as a linear combination")
+
+    def is_const(self):
+        return not self.t
+
+    def single_wire(self):
+        """wire id if this is exactly 1 * wire, else None"""
+        if self.k == 0 and len(self.t) == 1:
+            (w, c), = self.t.items()
+            if c == 1:
+                return w
+        return None
+
+    def __add__(self, o):
+        if isinstance(o, Quad):
+            return o + self
+        o = LC.of(o)
+        if not o.t:
+            return LC(self.t, self.k + o.k)
+        if not self.t:
+            return LC(o.t, self.k + o.k)
+        t = dict(self.t)
+        for w, c in o.t.items():
+            v = (t.get(w, 0) + c) % R
+            if v:
+                t[w] = v
+            else:
+                t.pop(w, None)
+        return LC(t, self.k + o.k)
+
+    __radd__ = __add__
+
+    def __neg__(self):
+        return LC({w: R - c for w, c in self.t.items()}, -self.k)
+
+    def __sub__(self, o):
+        if isinstance(o, Quad):
+            return (-o) + self
+        return self + (-LC.of(o))
+
+    def __rsub__(self, o):
+        return LC.of(o) + (-self)
+
+    def __mul__(self, o):
+        if isinstance(o, int):
+            o %= R
+            if o == 0:
+                return LC()
+            if o == 1:
+                return self
+            return LC({w: c * o % R for w, c in self.t.items()}, self.k * o)
+        if isinstance(o, LC):
+            if not o.t:
+                return self * o.k
+            if not self.t:
+                return o * self.k
+            return Quad(self, o, LC())
+        return NotImplemented
+
+    __rmul__ = __mul__
+
+
+class Quad:
+    """a * b + c with a, b, c linear -- what one R1CS constraint can express."""
+    __slots__ = ("a", "b", "c")
+
+    def __init__(self, a, b, c):
+        self.a, self.b, self.c = a, b, c
+
+    def __add__(self, o):
+        if isinstance(o, Quad):
+            raise ValueError("non-quadratic expression: sum of two products")
+        return Quad(self.a, self.b, self.c + o)
+
+    __radd__ = __add__
+
+    def __sub__(self, o):
+        if isinstance(o, Quad):
+            raise ValueError("non-quadratic expression: difference of two products")
+        return Quad(self.a, self.b, self.c - o)
+
+    def __rsub__(self, o):
+        return (-self) + o
+
+    def __neg__(self):
+        return Quad(-self.a, self.b, -self.c)
+
+    def __mul__(self, o):
+        if isinstance(o, int):
+            return Quad(self.a * o, self.b, self.c * o)
+        if isinstance(o, LC) and o.is_const():
+            return self * o.k
+        raise ValueError("non-quadratic expression: product of degree > 2")
+
+    __rmul__ = __mul__
+
+
+def _terms(lc: LC):
+    """constraint-side representation: dict wire -> coef with the constant under wire 0"""
+    d = dict(lc.t)
+    if lc.k:
+        d[0] = lc.k
+    return d
+
+
+class Circuit:
+    def __init__(self, name):
+        self.name = name
+        self.n_wires = 1          # wire 0 == 1
+        self.n_temps = 0
+        self.outputs = []         # (name, dims, first wire)
+        self.inputs = []
+        self.n_out = 0
+        self.n_in = 0
+        self._io_closed = False
+        self.constraints = []     # (A, B, C) dicts
+        self.prog = []            # instruction tuples
+        self.output_assigned = set()
+
+    # ---- declaration -------------------------------------------------
+    @staticmethod
+    def _size(dims):
+        n = 1
+        for d in dims:
+            n *= d
+        return n
+
+    def output(self, name, *dims):
+        assert not self.inputs and not self._io_closed, "outputs come first in the witness"
+        n = self._size(dims)
+        first = self.n_wires
+        self.n_wires += n
+        self.n_out += n
+        self.outputs.append((name, dims, first))
+        return self._shape([LC({first + i: 1}) for i in range(n)], dims)
+
+    def input(self, name, *dims):
+        assert not self._io_closed
+        n = self._size(dims)
+        first = self.n_wires
+        self.n_wires += n
+        self.n_in += n
+        self.inputs.append((name, dims, first))
+        return self._shape([LC({first + i: 1}) for i in range(n)], dims)
+
+    @staticmethod
+    def _shape(flat, dims):
+        if not dims:
+            return flat[0]
+        if len(dims) == 1:
+            return flat
+        step = len(flat) // dims[0]
+        return [Circuit._shape(flat[i * step:(i + 1) * step], dims[1:]) for i in range(dims[0])]
+
+    # ---- wires ---------------------------------------------------------
+    def _new_wire(self):
+        self._io_closed = True
+        w = self.n_wires
+        self.n_wires += 1
+        return w
+
+    def _new_temp(self):
+        self.n_temps += 1
+        return -self.n_temps  # remapped behind the witness wires at finalisation
+
+    def mul(self, a, b):
+        """signal s; s <== a * b"""
+        return self.quad(LC.of(a) * LC.of(b))
+
+    def quad(self, q):
+        """signal s; s <== a*b + c   (one constraint).  Linear input: returned as is."""
+        if isinstance(q, (LC, int)):
+            return LC.of(q)
+        if q.a.is_const():
+            return q.b * q.a.k + q.c
+        if q.b.is_const():
+            return q.a * q.b.k + q.c
+        w = self._new_wire()
+        self.prog.append((OP_MUL, w, q.a, q.b, q.c))
+        self.constraints.append((_terms(q.a), _terms(q.b), _terms(LC({w: 1}) - q.c)))
+        return LC({w: 1})
+
+    def wire(self, x):
+        """force a real signal equal to x (s <== x)"""
+        if isinstance(x, Quad):
+            return self.quad(x)
+        x = LC.of(x)
+        if x.single_wire() is not None:
+            return x
+        w = self._new_wire()
+        self.prog.append((OP_LIN, w, x))
+        self.constraints.append(({}, {}, _terms(x - LC({w: 1}))))
+        return LC({w: 1})
+
+    def assign_output(self, out_lc, x):
+        """out <== x for a declared main output"""
+        w = out_lc.single_wire()
+        assert w is not None and 1 <= w <= self.n_out and w not in self.output_assigned
+        self.output_assigned.add(w)
+        self._io_closed = True
+        if isinstance(x, Quad) and not (x.a.is_const() or x.b.is_const()):
+            self.prog.append((OP_MUL, w, x.a, x.b, x.c))
+            self.constraints.append((_terms(x.a), _terms(x.b), _terms(out_lc - x.c)))
+            return
+        if isinstance(x, Quad):
+            x = x.a * x.b + x.c
+        x = LC.of(x)
+        self.prog.append((OP_LIN, w, x))
+        self.constraints.append(({}, {}, _terms(x - out_lc)))
+
+    def _src(self, x):
+        """single id (wire or temp) holding the value of x, for hint instructions"""
+        x = LC.of(x)
+        w = x.single_wire()
+        if w is not None:
+            return w
+        t = self._new_temp()
+        self.prog.append((OP_LIN, t, x))
+        return t
+
+    def hint_bits(self, x, n):
+        """out[i] <-- (x >> i) & 1, i < n   (no constraints)"""
+        self._io_closed = True
+        src = self._src(x)
+        first = self.n_wires
+        self.n_wires += n
+        self.prog.append((OP_BITS, first, src, n))
+        return [LC({first + i: 1}) for i in range(n)]
+
+    def hint_inv(self, x):
+        """inv <-- x != 0 ? 1/x : 0"""
+        src = self._src(x)
+        w = self._new_wire()
+        self.prog.append((OP_INV, w, src))
+        return LC({w: 1})
+
+    # ---- constraints ---------------------------------------------------
+    def assert_zero(self, x):
+        """x === 0 (constraint + run-time assert, circom_runtime error 4 "Assert Failed")"""
+        if isinstance(x, Quad) and not (x.a.is_const() or x.b.is_const()):
+            a, b, c = x.a, x.b, -x.c
+        else:
+            if isinstance(x, Quad):
+                x = x.a * x.b + x.c
+            x = LC.of(x)
+            if x.is_const():
+                if x.k != 0:
+                    raise ValueError("constraint is never satisfiable")
+                return
+            a, b, c = LC(), LC(), x
+        self.prog.append((OP_ASSERT, a, b, c))
+        self.constraints.append((_terms(a), _terms(b), _terms(c)))
+
+    def assert_eq(self, x, y):
+        self.assert_zero(x - y)
+
+    # ---- outputs -------------------------------------------------------
+    def finalize(self):
+        assert len(self.output_assigned) == self.n_out, f"{self.name}: unassigned main outputs"
+        return Compiled(self)
+
+
+class Compiled:
+    """Finalised circuit: R1CS + witness program with temps remapped and levels computed."""
+
+    def __init__(self, c: Circuit):
+        self.name = c.name
+        self.n_witness = c.n_wires
+        self.n_total = c.n_wires + c.n_temps
+        self.n_out, self.n_in = c.n_out, c.n_in
+        self.outputs, self.inputs = c.outputs, c.inputs
+        self.constraints = c.constraints
+        nw = c.n_wires
+
+        def rid(w):
+            return w if w >= 0 else nw + (-w - 1)
+
+        def rlc(lc):
+            if any(w < 0 for w in lc.t):
+                return LC({rid(w): v for w, v in lc.t.items()}, lc.k)
+            return lc
+
+        level = [0] * self.n_total
+        prog = []
+        lv = []
+        for ins in c.prog:
+            op = ins[0]
+            if op == OP_LIN:
+                lc = rlc(ins[2])
+                dst = rid(ins[1])
+                l = 1 + max((level[w] for w in lc.t), default=0)
+                level[dst] = l
+                prog.append((op, dst, lc))
+            elif op == OP_MUL:
+                a, b, cc = rlc(ins[2]), rlc(ins[3]), rlc(ins[4])
+                l = 1 + max((level[w] for lc in (a, b, cc) for w in lc.t), default=0)
+                level[ins[1]] = l
+                prog.append((op, ins[1], a, b, cc))
+            elif op == OP_BITS:
+                src = rid(ins[2])
+                l = 1 + level[src]
+                for i in range(ins[3]):
+                    level[ins[1] + i] = l
+                prog.append((op, ins[1], src, ins[3]))
+            elif op == OP_INV:
+                src = rid(ins[2])
+                l = 1 + level[src]
+                level[ins[1]] = l
+                prog.append((op, ins[1], src))
+            else:
+                a, b, cc = rlc(ins[1]), rlc(ins[2]), rlc(ins[3])
+                l = 1 + max((level[w] for lc in (a, b, cc) for w in lc.t), default=0)
+                prog.append((op, a, b, cc))
+            lv.append(l)
+        order = sorted(range(len(prog)), key=lambda i: lv[i])
+        self.prog = [prog[i] for i in order]
+        self.levels = [lv[i] for i in order]
+        self.n_levels = max(lv, default=0)
+
+    # ---- .r1cs ------------------------------------------
+    def r1cs_bytes(self):
+        body = bytearray()
+        pack_i = struct.Struct("<I").pack
+        cache = {}
+
+        def coef(c):
+            v = cache.get(c)
+            if v is None:
+                v = cache[c] = c.to_bytes(32, "little")
+            return v
+
+        for lcs in self.constraints:
+            for lc in lcs:
+                items = sorted(lc.items())
+                body += pack_i(len(items))
+                for w, c in items:
+                    body += pack_i(w)
+                    body += coef(c)
+        hdr = struct.pack("<I", 32) + R.to_bytes(32, "little")
+        hdr += struct.pack("<IIIIQI", self.n_witness, self.n_out, 0, self.n_in, self.n_witness, len(self.constraints))
+        import numpy as np
+        wmap = np.arange(self.n_witness, dtype="<u8").tobytes()
+        out = b"r1cs" + struct.pack("<II", 1, 3)
+        for sid, pl in ((1, hdr), (2, bytes(body)), (3, wmap)):
+            out += struct.pack("<IQ", sid, len(pl)) + pl
+        return out
+
+    # ---- witness program (.wprog) -----------------------------------------
+    def wprog_bytes(self):
+        """Layout (all u32 little-endian unless noted):
+        "NZWP", version=1, n_total, n_witness, n_out, n_in, n_consts, n_instr, n_levels, n_code
+        consts   n_consts x 32 B canonical LE   (index 0 = 1, index 1 = r-1)
+        ioff     n_instr offsets into code (instructions sorted by level)
+        lstart   n_levels + 1 indices into ioff
+        code     instruction words:
+           LIN    op, dst, <lc>
+           MUL    op, dst, <lc a>, <lc b>, <lc c>
+           BITS   op, dst0, src, n
+           INV    op, dst, src
+           ASSERT op, <lc a>, <lc b>, <lc c>
+           <lc> = n_terms, const_idx (0xffffffff = no constant), then n_terms x (wire, coef_idx)"""
+        consts = {1: 0, R - 1: 1}
+        clist = [1, R - 1]
+
+        def cidx(v):
+            i = consts.get(v)
+            if i is None:
+                i = consts[v] = len(clist)
+                clist.append(v)
+            return i
+
+        code = []
+        ioff = []
+
+        def emit_lc(lc):
+            code.append(len(lc.t))
+            code.append(cidx(lc.k) if lc.k else 0xFFFFFFFF)
+            for w in sorted(lc.t):
+                code.append(w)
+                code.append(cidx(lc.t[w]))
+
+        for ins in self.prog:
+            ioff.append(len(code))
+            op = ins[0]
+            code.append(op)
+            if op == OP_LIN:
+                code.append(ins[1])
+                emit_lc(ins[2])
+            elif op == OP_MUL:
+                code.append(ins[1])
+                emit_lc(ins[2]); emit_lc(ins[3]); emit_lc(ins[4])
+            elif op == OP_BITS:
+                code.extend((ins[1], ins[2], ins[3]))
+            elif op == OP_INV:
+                code.extend((ins[1], ins[2]))
+            else:
+                emit_lc(ins[1]); emit_lc(ins[2]); emit_lc(ins[3])
+        lstart = [0] * (self.n_levels + 1)
+        for l in self.levels:
+            lstart[l] += 1  # count at index l (levels are 1-based) -> prefix below
+        acc = 0
+        starts = []
+        for l in range(1, self.n_levels + 1):
+            starts.append(acc)
+            acc += lstart[l]
+        starts.append(acc)
+        import numpy as np
+        hdr = b"NZWP" + struct.pack("<IIIIIIIII", 1, self.n_total, self.n_witness, self.n_out, self.n_in, len(clist),
+                                    len(self.prog), self.n_levels, len(code))
+        return (hdr + b"".join(v.to_bytes(32, "little") for v in clist) + np.asarray(ioff, dtype="<u4").tobytes() +
+                np.asarray(starts, dtype="<u4").tobytes() + np.asarray(code, dtype="<u4").tobytes())
+
+    def artifact(self):
+        """the build products a circom run leaves on disk: .r1cs, witness program, I/O table"""
+        return Artifact(self.name, self.n_witness, self.n_total, self.n_out, self.n_in, list(self.inputs),
+                        list(self.outputs), len(self.constraints), self.n_levels, len(self.prog), self.wprog_bytes(),
+                        self.r1cs_bytes())
+
+    def flatten_input(self, inp: dict):
+        return flatten_input(self.inputs, inp)
+
+
+class Artifact:
+    def __init__(self, name, n_witness, n_total, n_out, n_in, inputs, outputs, n_constraints, n_levels, n_instr, wprog,
+                 r1cs):
+        self.name, self.n_witness, self.n_total, self.n_out, self.n_in = name, n_witness, n_total, n_out, n_in
+        self.inputs, self.outputs = inputs, outputs
+        self.n_constraints, self.n_levels, self.n_instr = n_constraints, n_levels, n_instr
+        self.wprog, self.r1cs = wprog, r1cs
+
+    def wprog_bytes(self):
+        return self.wprog
+
+    def r1cs_bytes(self):
+        return self.r1cs
+
+    def flatten_input(self, inp: dict):
+        return flatten_input(self.inputs, inp)
+
+
+# ---- input marshalling (circom_runtime: names, arrays flattened row-major) --
+def flatten_input(inputs, inp: dict):
+    vals = []
+    for name, dims, _first in inputs:
+        if name not in inp:
+            raise KeyError(f"Signal not found: {name}")  # circom_runtime error 1
+        flat = []
+
+        def walk(x):
+            if isinstance(x, (list, tuple)):
+                for y in x:
+                    walk(y)
+            else:
+                flat.append(int(x) % R)
+
+        walk(inp[name])
+        n = Circuit._size(dims)
+        if len(flat) > n:
+            raise ValueError(f"Too many values for input signal {name}")  # error 2 / 6
+        if len(flat) < n:
+            raise ValueError(f"Not enough values for input signal {name}")
+        vals.extend(flat)
+    extra = set(inp) - {n for n, _, _ in inputs}
+    if extra:
+        raise KeyError(f"Signal not found: {sorted(extra)[0]}")
+    return vals

@@ -483,7 +483,7 @@ extern "C" int32_t nzcb_zkey_load(nzcb_ctx* ctx, const uint8_t* data, size_t len
 namespace {
 
 struct Bufs {
-    Fr *w_le, *W, *A, *B, *C, *pol_a, *pol_b, *pol_c, *pol_z, *A4, *B4, *C4, *Z4, *num, *den, *T, *Tz, *pol_r, *pol_wxi,
+    Fr *W, *A, *B, *C, *pol_a, *pol_b, *pol_c, *pol_z, *A4, *B4, *C4, *Z4, *num, *den, *T, *Tz, *pol_r, *pol_wxi,
         *quot, *vals, *pub;
     G1XYZZ* pts;
     int* flags;
@@ -497,7 +497,6 @@ struct Bufs {
 
 int get_bufs(nzcb_ctx* ctx, const nzcb_zkey* zk, Bufs& b) {
     const size_t n = zk->n;
-    GETBUF(w_le, "pv_w_le", zk->n_vars);
     GETBUF(W, "pv_W", zk->n_vars + 1);
     GETBUF(A, "pv_A", n);
     GETBUF(B, "pv_B", n);
@@ -524,6 +523,38 @@ int get_bufs(nzcb_ctx* ctx, const nzcb_zkey* zk, Bufs& b) {
     return 0;
 }
 
+// NZCB_TRACE=1: per-phase device times (CUDA events on the ctx stream) to stderr
+struct Tracer {
+    nzcb_ctx* ctx;
+    bool on;
+    std::vector<std::pair<const char*, cudaEvent_t>> marks;
+    explicit Tracer(nzcb_ctx* c) : ctx(c) {
+        const char* e = getenv("NZCB_TRACE");
+        on = e && e[0] == '1';
+        mark("start");
+    }
+    void mark(const char* name) {
+        if (!on) return;
+        cudaEvent_t ev;
+        cudaEventCreate(&ev);
+        cudaEventRecord(ev, ctx->stream);
+        marks.push_back({name, ev});
+    }
+    ~Tracer() {
+        if (!on) return;
+        cudaStreamSynchronize(ctx->stream);
+        for (size_t i = 1; i < marks.size(); i++) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, marks[i - 1].second, marks[i].second);
+            fprintf(stderr, "[nzcb trace] %-14s %9.3f ms\n", marks[i].first, ms);
+        }
+        float tot = 0;
+        if (marks.size() > 1) cudaEventElapsedTime(&tot, marks.front().second, marks.back().second);
+        fprintf(stderr, "[nzcb trace] %-14s %9.3f ms\n", "total", tot);
+        for (auto& m : marks) cudaEventDestroy(m.second);
+    }
+};
+
 // evaluations -> (blinded coefficient polynomial, unblinded 4n evaluations)   [snarkjs to4T]
 int to4t(nzcb_ctx* ctx, const nzcb_zkey* zk, const Fr* d_evals, Fr* d_pol, Fr* d_ext, const Fr* pz, int k) {
     const size_t n = zk->n;
@@ -537,6 +568,11 @@ int to4t(nzcb_ctx* ctx, const nzcb_zkey* zk, const Fr* d_evals, Fr* d_pol, Fr* d
     NZ_LAUNCH(ctx, k_blind, 1, 32, 0, d_pol, n, bl);
     return 0;
 }
+
+// d_w_le: device, n_w canonical little-endian witness values (NOT yet Montgomery); may alias b.w_le.
+// h_pub_le: host copy of w[1..nPublic] (canonical LE) for the transcript.
+int prove_core(nzcb_ctx* ctx, const nzcb_zkey* zk, const Fr* d_w_le, const uint8_t* h_pub_le, const uint8_t* blinders_le,
+               nzcb_proof* out, uint8_t* public_le);
 
 int prove_one(nzcb_ctx* ctx, const nzcb_zkey* zk, const uint8_t* wtns, size_t wtns_len, const uint8_t* blinders_le,
               nzcb_proof* out, uint8_t* public_le) {
@@ -554,9 +590,18 @@ int prove_one(nzcb_ctx* ctx, const nzcb_zkey* zk, const uint8_t* wtns, size_t wt
     if (n_wit != n_w || ws[2].size != (uint64_t)n_wit * 32)
         return ctx->fail(NZCB_E_WITNESS, "Invalid witness length. Circuit: %u, witness: %u, %u", zk->n_vars, n_wit,
                          zk->n_add);
+    if (zk->n_public + 1 > n_w) return ctx->fail(NZCB_E_WITNESS, "Invalid witness length: fewer values than public signals");
     const uint8_t* wv = ws[2].p;
+    Fr* d_w = (Fr*)ctx->scratch_get("pv_w_le", (size_t)zk->n_vars * sizeof(Fr));
+    if (!d_w) return ctx->fail(NZCB_E_NOMEM, "prove: cannot allocate the witness buffer");
+    NZ_CUDA(ctx, cudaMemcpyAsync(d_w, wv, (size_t)n_w * 32, cudaMemcpyHostToDevice, ctx->stream));
+    return prove_core(ctx, zk, d_w, wv + 32, blinders_le, out, public_le);
+}
+
+int prove_core(nzcb_ctx* ctx, const nzcb_zkey* zk, const Fr* d_w_le, const uint8_t* h_pub_le, const uint8_t* blinders_le,
+               nzcb_proof* out, uint8_t* public_le) {
+    const uint32_t n_w = zk->n_vars - zk->n_add;
     const uint32_t n = zk->n, n_pub = zk->n_public;
-    if (n_pub + 1 > n_w) return ctx->fail(NZCB_E_WITNESS, "Invalid witness length: fewer values than public signals");
 
     // blinders b1..b9 (Montgomery); index 0 unused
     Fr bl[10];
@@ -584,14 +629,15 @@ int prove_one(nzcb_ctx* ctx, const nzcb_zkey* zk, const uint8_t* wtns, size_t wt
     Bufs b;
     NZ_TRY(get_bufs(ctx, zk, b));
     NZ_CUDA(ctx, cudaMemsetAsync(b.flags, 0, 4 * sizeof(int), ctx->stream));
-    NZ_CUDA(ctx, cudaMemcpyAsync(b.w_le, wv, (size_t)n_w * 32, cudaMemcpyHostToDevice, ctx->stream));
-    NZ_LAUNCH(ctx, k_wtns_to_mont, div_up(n_w, 256), 256, 0, b.w_le, b.W, (size_t)n_w);
+    NZ_LAUNCH(ctx, k_wtns_to_mont, div_up(n_w, 256), 256, 0, d_w_le, b.W, (size_t)n_w);
+    Tracer tr_(ctx);
     for (size_t l = 0; l + 1 < zk->level_off.size(); l++) {
         const uint32_t lo = zk->level_off[l], hi = zk->level_off[l + 1];
         if (hi > lo)
             NZ_LAUNCH(ctx, k_additions, div_up(hi - lo, 256), 256, 0, zk->d_add_a, zk->d_add_b, zk->d_add_ac,
                       zk->d_add_bc, zk->d_add_out, lo, hi, zk->n_vars, n_w, b.W);
     }
+    tr_.mark("wtns+additions");
     // ---- round 1
     NZ_LAUNCH(ctx, k_gather, div_up(n, 256), 256, 0, zk->d_map[0], b.W, zk->n_vars, zk->n_cons, n, b.A);
     NZ_LAUNCH(ctx, k_gather, div_up(n, 256), 256, 0, zk->d_map[1], b.W, zk->n_vars, zk->n_cons, n, b.B);
@@ -602,6 +648,7 @@ int prove_one(nzcb_ctx* ctx, const nzcb_zkey* zk, const uint8_t* wtns, size_t wt
         NZ_TRY(to4t(ctx, zk, b.B, b.pol_b, b.B4, pb, 2));
         NZ_TRY(to4t(ctx, zk, b.C, b.pol_c, b.C4, pc, 2));
     }
+    tr_.mark("r1 ntt");
     G1Affine cA, cB, cC, cZ, cT1, cT2, cT3, cWxi, cWxiw;
     NZ_TRY(msm_dev(ctx, zk->d_ptau, (const uint32_t*)b.pol_a, (size_t)n + 2, true, b.pts + 0));
     NZ_TRY(msm_to_host_affine(ctx, b.pts + 0, &cA));
@@ -613,17 +660,18 @@ int prove_one(nzcb_ctx* ctx, const nzcb_zkey* zk, const uint8_t* wtns, size_t wt
     g1_to_be(cB, out->B);
     g1_to_be(cC, out->C);
 
+    tr_.mark("r1 msm x3");
     // ---- round 2
     std::vector<uint8_t> tr;
     std::vector<Fr> pub_m(n_pub + 1);
     for (uint32_t i = 0; i < n_pub; i++) {
-        const Fr v = fr_from_le(wv + (size_t)(i + 1) * 32);  // A[i] = w[i+1] for the public-input gates
+        const Fr v = fr_from_le(h_pub_le + (size_t)i * 32);  // A[i] = w[i+1] for the public-input gates
         if (!fr_is_canonical(v)) return ctx->fail(NZCB_E_WITNESS, "witness value %u is not reduced", i + 1);
         pub_m[i] = v.to_mont();
         uint8_t be[32];
         to_be_bytes(pub_m[i], be);
         append(tr, be, 32);
-        if (public_le) memcpy(public_le + (size_t)i * 32, wv + (size_t)(i + 1) * 32, 32);
+        if (public_le) memcpy(public_le + (size_t)i * 32, h_pub_le + (size_t)i * 32, 32);
     }
     append(tr, out->A, 64);
     append(tr, out->B, 64);
@@ -661,14 +709,17 @@ int prove_one(nzcb_ctx* ctx, const nzcb_zkey* zk, const uint8_t* wtns, size_t wt
         NZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         if (total != Fr::one()) return ctx->fail(NZCB_E_COPY, "Copy constraints does not match");
     }
+    tr_.mark("r2 grandprod");
     {
         const Fr pz[3] = {bl[9], bl[8], bl[7]};
         NZ_TRY(to4t(ctx, zk, b.den, b.pol_z, b.Z4, pz, 3));
     }
+    tr_.mark("r2 ntt");
     NZ_TRY(msm_dev(ctx, zk->d_ptau, (const uint32_t*)b.pol_z, (size_t)n + 3, true, b.pts + 0));
     NZ_TRY(msm_to_host_affine(ctx, b.pts + 0, &cZ));
     g1_to_be(cZ, out->Z);
 
+    tr_.mark("r2 msm");
     // ---- round 3
     const Fr alpha = hash_to_fr(std::vector<uint8_t>(out->Z, out->Z + 64));
     const Fr alpha2 = alpha * alpha;
@@ -689,6 +740,7 @@ int prove_one(nzcb_ctx* ctx, const nzcb_zkey* zk, const uint8_t* wtns, size_t wt
         g.n = n; g.power = zk->power; g.n_pub = n_pub; g.T = b.T; g.Tz = b.Tz;
         NZ_LAUNCH(ctx, k_round3, div_up(4 * N, 128), 128, 0, g);
     }
+    tr_.mark("r3 quotient");
     NZ_TRY(ntt_dev(ctx, b.T, zk->power + 2, true));
     NZ_LAUNCH(ctx, k_div_zh, div_up(n, 256), 256, 0, b.T, n, b.flags);
     NZ_TRY(ntt_dev(ctx, b.Tz, zk->power + 2, true));
@@ -700,6 +752,7 @@ int prove_one(nzcb_ctx* ctx, const nzcb_zkey* zk, const uint8_t* wtns, size_t wt
         if (fl[0]) return ctx->fail(NZCB_E_DIVIDE, "T Polynomial is not divisible");
         if (fl[1]) return ctx->fail(NZCB_E_DIVIDE, "Tz Polynomial is not well calculated");
     }
+    tr_.mark("r3 intt x2");
     Fr* pol_t = b.T;  // 3n + 6 coefficients
     NZ_TRY(msm_dev(ctx, zk->d_ptau, (const uint32_t*)pol_t, N, true, b.pts + 0));
     NZ_TRY(msm_to_host_affine(ctx, b.pts + 0, &cT1));
@@ -711,6 +764,7 @@ int prove_one(nzcb_ctx* ctx, const nzcb_zkey* zk, const uint8_t* wtns, size_t wt
     g1_to_be(cT2, out->T2);
     g1_to_be(cT3, out->T3);
 
+    tr_.mark("r3 msm x3");
     // ---- round 4
     tr.clear();
     append(tr, out->T1, 64);
@@ -758,6 +812,7 @@ int prove_one(nzcb_ctx* ctx, const nzcb_zkey* zk, const uint8_t* wtns, size_t wt
     to_be_bytes(ezw, out->eval_zw);
     to_be_bytes(er, out->eval_r);
 
+    tr_.mark("r4 evals");
     // ---- round 5
     tr.clear();
     append(tr, out->eval_a, 32);
@@ -781,6 +836,7 @@ int prove_one(nzcb_ctx* ctx, const nzcb_zkey* zk, const uint8_t* wtns, size_t wt
         NZ_LAUNCH(ctx, k_pol_wxi, div_up(n + 6, 256), 256, 0, g);
     }
     NZ_TRY(poly_horner(ctx, b.pol_wxi, N + 6, xi, b.vals + 9, b.quot));
+    tr_.mark("r5 wxi poly");
     NZ_TRY(msm_dev(ctx, zk->d_ptau, (const uint32_t*)b.quot, N + 6, true, b.pts + 0));
     NZ_TRY(msm_to_host_affine(ctx, b.pts + 0, &cWxi));
     // W_{xi w} = (pol_z - eval_zw) / (X - xi w)
@@ -789,6 +845,7 @@ int prove_one(nzcb_ctx* ctx, const nzcb_zkey* zk, const uint8_t* wtns, size_t wt
     NZ_TRY(poly_horner(ctx, b.pol_wxi, N + 3, xiw, b.vals + 10, b.quot));
     NZ_TRY(msm_dev(ctx, zk->d_ptau, (const uint32_t*)b.quot, N + 3, true, b.pts + 1));
     NZ_TRY(msm_to_host_affine(ctx, b.pts + 1, &cWxiw));
+    tr_.mark("r5 rest");
     Fr rem[2];
     NZ_CUDA(ctx, cudaMemcpyAsync(rem, b.vals + 9, 2 * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
     NZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -838,6 +895,70 @@ extern "C" int32_t nzcb_plonk_prove_batch(nzcb_ctx* ctx, const nzcb_zkey* zk, co
     NZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1);
     return status ? 0 : first_err;
+}
+
+// witness.cu
+namespace nzcb {
+int witness_dev(nzcb_ctx* ctx, const nzcb_circuit* c, const Fr* d_inputs, size_t B, Fr* d_wires, int32_t* d_status);
+uint32_t circuit_n_total(const nzcb_circuit* c);
+uint32_t circuit_n_witness(const nzcb_circuit* c);
+uint32_t circuit_n_in(const nzcb_circuit* c);
+}  // namespace nzcb
+
+// snarkjs plonk.fullProve: witness program on the GPU, the wires never leave HBM, then the prover
+extern "C" int32_t nzcb_plonk_fullprove_batch(nzcb_ctx* ctx, const nzcb_circuit* cir, const nzcb_zkey* zk,
+                                              const uint8_t* inputs_le, size_t B, const uint8_t* blinders_le,
+                                              nzcb_proof* out, uint8_t* public_le, int32_t* status) {
+    if (!ctx || !cir || !zk || !out || !status || (!inputs_le && circuit_n_in(cir))) return NZCB_E_INVALID;
+    if (zk->ctx != ctx) return ctx->fail(NZCB_E_INVALID, "zkey was loaded on a different context");
+    const uint32_t n_w = zk->n_vars - zk->n_add;
+    if (circuit_n_witness(cir) != n_w)
+        return ctx->fail(NZCB_E_WITNESS, "Invalid witness length. Circuit: %u, witness: %u, %u", zk->n_vars,
+                         circuit_n_witness(cir), zk->n_add);
+    NZ_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t n_total = circuit_n_total(cir), n_in = circuit_n_in(cir), n_pub = zk->n_public;
+    const size_t per_pass = n_total * sizeof(Fr);
+    size_t chunk = std::max<size_t>(1, ((size_t)4 << 30) / per_pass);
+    if (chunk > B) chunk = B;
+    Fr* d_w = (Fr*)ctx->scratch_get("fp_wires", chunk * per_pass);
+    Fr* d_in = (Fr*)ctx->scratch_get("fp_inputs", std::max<size_t>(32, chunk * n_in * sizeof(Fr)));
+    int32_t* d_st = (int32_t*)ctx->scratch_get("fp_status", chunk * sizeof(int32_t));
+    if (!d_w || !d_in || !d_st) return ctx->fail(NZCB_E_NOMEM, "fullProve: cannot allocate the witness buffers");
+    std::vector<uint8_t> pub(std::max<size_t>(1, n_pub) * 32);
+    cudaEventRecord(ctx->ev0, ctx->stream);
+    for (size_t done = 0; done < B; done += chunk) {
+        const size_t nb = std::min(chunk, B - done);
+        if (n_in)
+            NZ_CUDA(ctx, cudaMemcpyAsync(d_in, inputs_le + done * n_in * 32, nb * n_in * 32, cudaMemcpyHostToDevice,
+                                         ctx->stream));
+        NZ_TRY(witness_dev(ctx, cir, d_in, nb, d_w, d_st));
+        NZ_CUDA(ctx, cudaMemcpyAsync(status + done, d_st, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        NZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        for (size_t i = 0; i < nb; i++) {
+            const size_t g = done + i;
+            if (status[g] != 0) {  // "Assert Failed": this pass is rejected, the batch goes on
+                memset(out + g, 0, sizeof(nzcb_proof));
+                continue;
+            }
+            const Fr* w = d_w + i * n_total;
+            if (n_pub) {
+                NZ_CUDA(ctx, cudaMemcpyAsync(pub.data(), w + 1, n_pub * 32, cudaMemcpyDeviceToHost, ctx->stream));
+                NZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            }
+            const int rc = prove_core(ctx, zk, w, pub.data(), blinders_le ? blinders_le + g * 9 * 32 : nullptr, out + g,
+                                      public_le ? public_le + g * n_pub * 32 : nullptr);
+            status[g] = rc;
+            if (rc != 0) {
+                cudaStreamSynchronize(ctx->stream);
+                if (rc == NZCB_E_CUDA || rc == NZCB_E_NOMEM) return rc;
+                memset(out + g, 0, sizeof(nzcb_proof));
+            }
+        }
+    }
+    cudaEventRecord(ctx->ev1, ctx->stream);
+    NZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1);
+    return 0;
 }
 
 // ------------------------------------------------------------------ proof.json
