@@ -97,6 +97,11 @@ int32_t nzcb_srs_g1(nzcb_ctx* ctx, const uint8_t tau_le[32], size_t count, uint8
 int32_t nzcb_plonk_setup(nzcb_ctx* ctx, const uint8_t* r1cs, size_t r1cs_len, const uint8_t* srs_g1_lem,
                          size_t srs_count, const uint8_t x2_g2_lem[128], uint8_t* zkey_out, size_t* zkey_len);
 
+/* what the R1CS -> PLONK expansion of `plonk setup` yields for this r1cs: gate count, additions,
+ * PLONK signal count and log2 of the domain (so the caller can size the SRS: 2^power + 6 points) */
+int32_t nzcb_plonk_setup_info(nzcb_ctx* ctx, const uint8_t* r1cs, size_t r1cs_len, uint32_t* n_gates,
+                              uint32_t* n_additions, uint32_t* plonk_vars, uint32_t* power);
+
 /* ---- prover: snarkjs plonk.prove(zkey, wtns) ---------------------------- */
 /* parse a PLONK zkey (v1, 14 sections) and make it device resident once */
 int32_t nzcb_zkey_load(nzcb_ctx* ctx, const uint8_t* zkey, size_t len, nzcb_zkey** out);

@@ -56,6 +56,7 @@ SIGNATURES = {
     "nzcb_msm_g1_dev": (_i32, [_vp, _vp, _vp, _sz, _vp]),
     "nzcb_srs_g1": (_i32, [_vp, _vp, _sz, _vp]),
     "nzcb_plonk_setup": (_i32, [_vp, _vp, _sz, _vp, _sz, _vp, _vp, ctypes.POINTER(_sz)]),
+    "nzcb_plonk_setup_info": (_i32, [_vp, _vp, _sz] + [ctypes.POINTER(_u32)] * 4),
     "nzcb_zkey_load": (_i32, [_vp, _vp, _sz, ctypes.POINTER(_vp)]),
     "nzcb_zkey_free": (None, [_vp]),
     "nzcb_zkey_info": (_i32, [_vp] + [ctypes.POINTER(_u32)] * 5),
@@ -148,6 +149,17 @@ class Context:
         buf = (ctypes.c_uint8 * nbytes)()
         self.check(self.lib.nzcb_dev_download(self.h, buf, p, nbytes))
         return bytes(buf)
+
+
+def as_cbuf(data):
+    """zero-copy read-only view of a bytes object for the C ABI (borrowed for the call only)"""
+    if isinstance(data, ctypes.Array):
+        return data
+    if isinstance(data, bytes):
+        return ctypes.cast(ctypes.c_char_p(data), ctypes.c_void_p)
+    if isinstance(data, bytearray):
+        return (ctypes.c_uint8 * len(data)).from_buffer(data)
+    return (ctypes.c_uint8 * len(data)).from_buffer_copy(bytes(data))
 
 
 _default_ctx = {}

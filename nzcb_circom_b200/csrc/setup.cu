@@ -70,7 +70,7 @@ struct Term {
 typedef std::vector<Term> LC;
 
 struct Plan {
-    const uint8_t* key_ptr = nullptr;
+    uint64_t key_hash = 0;
     size_t key_len = 0;
     uint32_t n_public = 0, r1cs_vars = 0, plonk_vars = 0, power = 0;
     std::vector<uint32_t> sl, sr, so;
@@ -272,8 +272,28 @@ int build_plan(nzcb_ctx* ctx, const uint8_t* r1cs, size_t len, Plan& p) {
     while (((size_t)1 << power) < ng) power++;  // = log2(ng - 1) + 1 for ng >= 2
     if (power < 3) power = 3;
     p.power = power;
-    p.key_ptr = r1cs;
+    p.key_hash = 0;
     p.key_len = len;
+    return 0;
+}
+
+// cheap identity of an r1cs buffer (length + FNV-1a over a strided sample) so the size query and
+// the real call of nzcb_plonk_setup share one gate expansion even when the caller re-marshals
+uint64_t r1cs_fingerprint(const uint8_t* d, size_t len) {
+    uint64_t h = 1469598103934665603ull ^ len;
+    const size_t step = len > (1u << 20) ? 4099 : 1;
+    for (size_t i = 0; i < len; i += step) h = (h ^ d[i]) * 1099511628211ull;
+    for (size_t i = len > 4096 ? len - 4096 : 0; i < len; i++) h = (h ^ d[i]) * 1099511628211ull;
+    return h;
+}
+
+int get_plan(nzcb_ctx* ctx, const uint8_t* r1cs, size_t len, Plan** out) {
+    const uint64_t fp = r1cs_fingerprint(r1cs, len);
+    if (g_plan.key_len != len || g_plan.key_hash != fp || g_plan.sl.empty()) {
+        NZ_TRY(build_plan(ctx, r1cs, len, g_plan));
+        g_plan.key_hash = fp;
+    }
+    *out = &g_plan;
     return 0;
 }
 
@@ -302,11 +322,24 @@ extern "C" int32_t nzcb_srs_g1(nzcb_ctx* ctx, const uint8_t tau_le[32], size_t c
     return 0;
 }
 
+extern "C" int32_t nzcb_plonk_setup_info(nzcb_ctx* ctx, const uint8_t* r1cs, size_t r1cs_len, uint32_t* n_gates,
+                                         uint32_t* n_additions, uint32_t* plonk_vars, uint32_t* power) {
+    if (!ctx || !r1cs) return NZCB_E_INVALID;
+    Plan* p = nullptr;
+    NZ_TRY(get_plan(ctx, r1cs, r1cs_len, &p));
+    if (n_gates) *n_gates = (uint32_t)p->sl.size();
+    if (n_additions) *n_additions = (uint32_t)p->add_a.size();
+    if (plonk_vars) *plonk_vars = p->plonk_vars;
+    if (power) *power = p->power;
+    return 0;
+}
+
 extern "C" int32_t nzcb_plonk_setup(nzcb_ctx* ctx, const uint8_t* r1cs, size_t r1cs_len, const uint8_t* srs,
                                     size_t srs_count, const uint8_t x2[128], uint8_t* zkey_out, size_t* zkey_len) {
     if (!ctx || !r1cs || !zkey_len) return NZCB_E_INVALID;
-    Plan& p = g_plan;
-    if (p.key_ptr != r1cs || p.key_len != r1cs_len || p.sl.empty()) NZ_TRY(build_plan(ctx, r1cs, r1cs_len, p));
+    Plan* pp = nullptr;
+    NZ_TRY(get_plan(ctx, r1cs, r1cs_len, &pp));
+    Plan& p = *pp;
     const size_t need = p.zkey_size();
     if (!zkey_out) {
         *zkey_len = need;

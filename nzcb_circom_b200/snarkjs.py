@@ -19,7 +19,7 @@ import ctypes
 import json
 import struct
 
-from ._lib import NzcbError, Proof, default_context
+from ._lib import NzcbError, Proof, as_cbuf, default_context
 
 R_MOD = 0x30644e72e131a029b85045b68181585d2833e84879b9709143e1f593f0000001
 
@@ -28,7 +28,11 @@ _EVALS = ("eval_a", "eval_b", "eval_c", "eval_s1", "eval_s2", "eval_zw", "eval_r
 
 
 def _bytes_of(x):
-    if isinstance(x, (bytes, bytearray, memoryview)):
+    if isinstance(x, bytes):
+        return x
+    if isinstance(x, bytearray):
+        return x
+    if isinstance(x, memoryview):
         return bytes(x)
     with open(x, "rb") as f:
         return f.read()
@@ -41,8 +45,7 @@ class ZKey:
         self.ctx = ctx or default_context()
         data = _bytes_of(zkey)
         h = ctypes.c_void_p()
-        buf = (ctypes.c_uint8 * len(data)).from_buffer_copy(data)
-        self.ctx.check(self.ctx.lib.nzcb_zkey_load(self.ctx.h, buf, len(data), ctypes.byref(h)))
+        self.ctx.check(self.ctx.lib.nzcb_zkey_load(self.ctx.h, as_cbuf(data), len(data), ctypes.byref(h)))
         self.h = h
         vals = [ctypes.c_uint32() for _ in range(5)]
         self.ctx.lib.nzcb_zkey_info(self.h, *[ctypes.byref(v) for v in vals])
@@ -159,19 +162,118 @@ class _Plonk:
         tauG1 points, affine LEM, as section 2 of the .ptau holds them)."""
         ctx = ctx or default_context()
         r = _bytes_of(r1cs)
-        rbuf = (ctypes.c_uint8 * len(r)).from_buffer_copy(r)
-        sbuf = (ctypes.c_uint8 * len(srs_g1_lem)).from_buffer_copy(srs_g1_lem)
+        rbuf, sbuf = as_cbuf(r), as_cbuf(bytes(srs_g1_lem))
         x2 = (ctypes.c_uint8 * 128).from_buffer_copy(x2_g2_lem)
         n = ctypes.c_size_t(0)
         ctx.check(ctx.lib.nzcb_plonk_setup(ctx.h, rbuf, len(r), sbuf, len(srs_g1_lem) // 64, x2, None, ctypes.byref(n)))
-        out = (ctypes.c_uint8 * n.value)()
-        ctx.check(ctx.lib.nzcb_plonk_setup(ctx.h, rbuf, len(r), sbuf, len(srs_g1_lem) // 64, x2, out, ctypes.byref(n)))
-        return bytes(out)
+        out = bytearray(n.value)
+        obuf = (ctypes.c_uint8 * n.value).from_buffer(out)
+        ctx.check(ctx.lib.nzcb_plonk_setup(ctx.h, rbuf, len(r), sbuf, len(srs_g1_lem) // 64, x2, obuf, ctypes.byref(n)))
+        del obuf
+        return out
 
-    def fullProve(self, input, circuit, zkey, blinders=None, ctx=None):
-        """snarkjs.plonk.fullProve(input, wasmFile, zkeyFile): witness on the GPU, then prove."""
-        w = wtns.calculate(input, circuit, ctx=ctx)
-        return self.prove(zkey, w, blinders=blinders, ctx=ctx)
+    def setup_info(self, r1cs, ctx=None):
+        """(nGates, nAdditions, plonkNVars, power) of the R1CS -> PLONK expansion"""
+        ctx = ctx or default_context()
+        r = _bytes_of(r1cs)
+        v = [ctypes.c_uint32() for _ in range(4)]
+        ctx.check(ctx.lib.nzcb_plonk_setup_info(ctx.h, as_cbuf(r), len(r), *[ctypes.byref(x) for x in v]))
+        return tuple(x.value for x in v)
+
+    def fullProve(self, input, circuit, zkey, blinders=None, ctx=None, raw=False):
+        """snarkjs.plonk.fullProve(input, wasmFile, zkeyFile): witness program and prover fused on
+        the GPU (the wires never leave HBM).  `circuit` is a circom_tester.WasmTester."""
+        res = self.fullProveBatch([input], circuit, zkey, None if blinders is None else [blinders], ctx)
+        proof, public, status = res[0]
+        if status != 0:
+            c = ctx or default_context()
+            raise NzcbError(status, "Assert Failed" if status == -6 else c.lib.nzcb_last_error(c.h).decode())
+        return (proof, public) if raw else (proof_struct_to_obj(Proof.from_buffer_copy(proof)), public)
+
+    def fullProveBatch(self, inputs, circuit, zkey, blinders_list=None, ctx=None):
+        """B passes -> [(proof bytes | None, publicSignals, status)]; a rejected pass never fails the batch."""
+        ctx = ctx or (zkey.ctx if isinstance(zkey, ZKey) else default_context())
+        zk = _as_zkey(zkey, ctx)
+        art = circuit.compiled
+        h = circuit._handle(ctx)
+        flat = bytearray()
+        for inp in inputs:
+            vals = art.flatten_input(inp) if isinstance(inp, dict) else inp
+            flat += b"".join(int(v).to_bytes(32, "little") for v in vals)
+        return self.fullProveRaw(bytes(flat), len(inputs), h, zk, blinders_list, ctx)
+
+    def fullProveRaw(self, inputs_le, B, circuit_handle, zk, blinders_list=None, ctx=None):
+        """inputs already marshalled: B x nInputs x 32 B canonical LE"""
+        ctx = ctx or zk.ctx
+        ibuf = (ctypes.c_uint8 * max(1, len(inputs_le))).from_buffer_copy(inputs_le or b"\0")
+        bl = None
+        if blinders_list is not None:
+            raw = b"".join(int(x).to_bytes(32, "little") for bs in blinders_list for x in bs)
+            bl = (ctypes.c_uint8 * len(raw)).from_buffer_copy(raw)
+        out = (Proof * B)()
+        npub = max(1, zk.n_public)
+        pub = (ctypes.c_uint8 * (32 * npub * B))()
+        status = (ctypes.c_int32 * B)()
+        ctx.check(ctx.lib.nzcb_plonk_fullprove_batch(ctx.h, circuit_handle, zk.h, ibuf, B, bl, out, pub, status))
+        res = []
+        for i in range(B):
+            pb = bytes(pub[i * 32 * zk.n_public:(i + 1) * 32 * zk.n_public])
+            public = [str(int.from_bytes(pb[k * 32:(k + 1) * 32], "little")) for k in range(zk.n_public)]
+            res.append((bytes(out[i]) if status[i] == 0 else None, public, int(status[i])))
+        return res
+
+
+P_MOD = 0x30644e72e131a029b85045b68181585d97816a916871ca8d3c208c16d87cfd47
+
+
+class _ZKeyTools:
+    def exportVerificationKey(self, zkey):
+        """`snarkjs zkey export verificationkey` (/root/reference/Makefile:56,61): the vk object
+        snarkjs writes to verification_key.json, from the zkey header (section 2) alone."""
+        data = _bytes_of(zkey) if not isinstance(zkey, (bytes, bytearray)) else zkey
+        if data[:4] != b"zkey":
+            raise ValueError("zkey file: bad magic")
+        nsec = struct.unpack_from("<I", data, 8)[0]
+        pos = 12
+        hdr = None
+        for _ in range(nsec):
+            sid, size = struct.unpack_from("<IQ", data, pos)
+            pos += 12
+            if sid == 2:
+                hdr = data[pos:pos + size]
+                break
+            pos += size
+        if hdr is None:
+            raise ValueError("zkey file: no header section")
+        rinv_r = pow(1 << 256, -1, R_MOD)
+        rinv_q = pow(1 << 256, -1, P_MOD)
+
+        def fr(b):
+            return int.from_bytes(b, "little") * rinv_r % R_MOD
+
+        def fq(b):
+            return int.from_bytes(b, "little") * rinv_q % P_MOD
+
+        def g1(b):
+            if b == bytes(64):
+                return ["0", "1", "0"]
+            return [str(fq(b[:32])), str(fq(b[32:])), "1"]
+
+        n_vars, n_public, domain, n_add, n_cons = struct.unpack_from("<IIIII", hdr, 72)
+        power = domain.bit_length() - 1
+        vk = {"protocol": "plonk", "curve": "bn128", "nPublic": n_public, "power": power, "k1": str(fr(hdr[92:124])),
+              "k2": str(fr(hdr[124:156]))}
+        off = 156
+        for nm in ("Qm", "Ql", "Qr", "Qo", "Qc", "S1", "S2", "S3"):
+            vk[nm] = g1(hdr[off:off + 64])
+            off += 64
+        x2 = hdr[off:off + 128]
+        vk["X_2"] = [[str(fq(x2[0:32])), str(fq(x2[32:64]))], [str(fq(x2[64:96])), str(fq(x2[96:128]))], ["1", "0"]]
+        w = pow(5, (R_MOD - 1) >> 28, R_MOD)
+        for _ in range(28 - power):
+            w = w * w % R_MOD
+        vk["w"] = str(w)
+        return vk
 
 
 class _Powersoftau:
@@ -214,6 +316,7 @@ def wtns_from_raw(raw_le: bytes):
 
 
 plonk = _Plonk()
+zKey = _ZKeyTools()
 powersoftau = _Powersoftau()
 wtns = _Wtns()
-__all__ = ["plonk", "powersoftau", "wtns", "ZKey", "write_wtns", "wtns_from_raw", "json"]
+__all__ = ["plonk", "powersoftau", "wtns", "zKey", "ZKey", "write_wtns", "wtns_from_raw", "json"]

@@ -496,6 +496,17 @@ def verification_key(zkey: bytes):
     return vk
 
 
+def vk_from_json(j):
+    """verification_key.json object (decimal strings, `snarkjs zkey export verificationkey`) -> vk dict"""
+    vk = {"nPublic": int(j["nPublic"]), "power": int(j["power"]), "k1": int(j["k1"]), "k2": int(j["k2"]),
+          "w": int(j["w"]), "X_2": j.get("X_2")}
+    for nm in ("Qm", "Ql", "Qr", "Qo", "Qc", "S1", "S2", "S3"):
+        x, y, z = j[nm]
+        vk[nm] = None if z == "0" else (int(x), int(y))
+    assert vk["w"] == b.fr_root(vk["power"])
+    return vk
+
+
 def verify_with_trapdoor(vk, public, proof, tau):
     """plonk.verify with the final pairing e(W1, [tau]_2) == e(W2, [1]_2) replaced by the
     equivalent G1 identity tau * W1 == W2, valid because the SRS trapdoor tau is known."""

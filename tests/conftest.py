@@ -20,3 +20,13 @@ def ctx():
     c = Context(0)
     yield c
     c.close()
+
+
+@pytest.fixture(scope="session")
+def nzcp_live_prover(ctx):
+    """nzcp_live at full size (domain 2^21): circuit, synthetic SRS, GPU plonk setup, resident zkey."""
+    from nzcb_circom_b200.prover import NzcpProver, default_tau
+
+    pr = NzcpProver(live=True, tau=default_tau(), ctx=ctx)
+    pr.setup()
+    return pr

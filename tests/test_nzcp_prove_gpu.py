@@ -1,0 +1,65 @@
+"""Config 2 / config 5 at full size: nzcp_live PLONK proofs (domain 2^21) on the GPU.  The Python
+oracle cannot prove at this size, so parity is carried by size-independent properties: every proof
+is accepted by the oracle's verifier (known-trapdoor form of plonk.verify), the public signals are
+the hashlib expectations, proofs are deterministic under injected blinders, the .wtns path and the
+fused path give identical bytes, and a rejected pass does not poison its batch."""
+import hashlib
+import random
+
+import pytest
+
+from nzcb_circom_b200 import nzcp_helpers as H
+from oracle import bn254 as b
+from oracle import plonk as oplonk
+from oracle.keccak import hash_to_fr
+
+pytestmark = pytest.mark.gpu
+TAU = hash_to_fr(b"nzcb-b200-tau")
+
+
+def test_default_tau_is_the_documented_trapdoor():
+    from nzcb_circom_b200.prover import default_tau
+
+    assert default_tau() == TAU
+
+
+def test_nzcp_live_domain(nzcp_live_prover):
+    pr = nzcp_live_prover
+    assert pr.zk.domain_size == 1 << 21 and pr.zk.n_public == 3  # README.md:41 (power-21 ptau), nPublic = 3 outputs
+    assert pr.vk["power"] == 21 and pr.vk["k1"] == "2" and pr.vk["k2"] == "3"
+
+
+def test_nzcp_live_proofs_verify(nzcp_live_prover):
+    from nzcb_circom_b200.snarkjs import plonk, wtns_from_raw
+
+    pr = nzcp_live_prover
+    vk = oplonk.vk_from_json(pr.vk)
+    rng = random.Random(5)
+    passes = [H.synth_pass(s) for s in (10, 11, 12)]
+    bad = bytearray(passes[1]["toBeSigned"])
+    bad[30] = 0x65  # claims header is not a map -> the circuit rejects this pass
+    items = [(passes[0]["toBeSigned"], passes[0]["data"]), (bytes(bad), passes[1]["data"]),
+             (passes[2]["toBeSigned"], passes[2]["data"])]
+    blinders = [[rng.randrange(b.R_MOD) for _ in range(9)] for _ in items]
+    res = pr.prove_passes(items, blinders)
+    assert [s for _, _, s in res] == [0, -6, 0] and res[1][0] is None
+    for (proof, public, _), p in ((res[0], passes[0]), (res[2], passes[2])):
+        pub = [int(x) for x in public]
+        nh, th, exp, data = H.nzcp_decode_outputs(pub)
+        assert nh == hashlib.sha512(H.fitBytes(p["nullifier"].encode(), 64)).digest()[:32]
+        assert th == hashlib.sha256(p["toBeSigned"]).digest() and exp == p["exp"] and data == p["data"]
+        assert oplonk.verify_with_trapdoor(vk, pub, oplonk.proof_from_bytes(proof), TAU)
+        tampered = oplonk.proof_from_bytes(proof)
+        tampered["eval_zw"] = (tampered["eval_zw"] + 1) % b.R_MOD
+        assert not oplonk.verify_with_trapdoor(vk, pub, tampered, TAU)
+        assert not oplonk.verify_with_trapdoor(vk, [pub[0], pub[1], pub[2] ^ 1], oplonk.proof_from_bytes(proof), TAU)
+    # deterministic under injected blinders; different blinders -> different proof, same public signals
+    again = pr.prove_passes([items[0]], [blinders[0]])
+    assert again[0][0] == res[0][0]
+    other = pr.prove_passes([items[0]], None)
+    assert other[0][0] != res[0][0] and other[0][1] == res[0][1]
+    # the two API paths agree byte for byte: calculateWitness -> .wtns -> plonk.prove  vs  fused fullProve
+    raw, st = pr.tester.calculateWitnessBatch([H.nzcp_input(items[0][0], 351, items[0][1])], True, pr.ctx)
+    assert st == [0]
+    proof2, pub2 = plonk.prove(pr.zk, wtns_from_raw(raw), blinders=blinders[0], raw=True)
+    assert proof2 == res[0][0] and pub2 == res[0][1]
