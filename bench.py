@@ -1,0 +1,300 @@
+#!/usr/bin/env python
+"""bench.py -- nzcp_live PLONK proofs/s (BASELINE.json metric) on N B200s of one node.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl reference]
+
+One process per GPU (torchrun for N > 1; RANK / LOCAL_RANK / WORLD_SIZE from the env).  A "step" is
+one fused fullProve call (witness program + PLONK prover) over a batch of B synthetic
+nzcp_live passes per GPU; independent proofs are sharded over the ranks with no collective
+(SURVEY.md 8e), so scaling is weak.  Workload = BASELINE.json configs[1] ("nzcp_live single proof,
+351-byte ToBeSigned, synthetic pass") repeated B times per step.
+
+  value     device-resident: marshalled inputs already in HBM, timed with CUDA events on the ctx stream
+  e2e       through the public host API (NzcpProver.prove_passes -> C ABI) with host buffers: pass
+            marshalling, H2D of the inputs and D2H of proofs / public signals inside the timed region
+  roofline  dominant kernel k_msm_accum (MSM bucket accumulation): algorithmic IMAD32 (160 modmul per
+            MSM point x 264 IMAD32) / CUDA-event time, against the IMAD32 peak measured
+            live by the library's own microbenchmark (the path is integer-pipe bound: neither HBM nor
+            tensor cores; MEASURED_PEAKS.json has no integer figure, its HBM number is reported beside it)
+  cpu_baseline / --impl reference
+            the reference's own path (circom WASM witness + snarkjs on Node) cannot run here (no Node,
+            SURVEY.md 0.2); the stand-in is the C port of the oracle (oracle/c, OpenMP, all host
+            cores): kind "port".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "nzcp_live PLONK proofs/s"
+UNIT = "proofs/s"
+
+
+def _rank_env():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(int(r[1]) for r in self.rows if len(r) >= 9 and r[1].isdigit())
+        mx = [int(r[2]) for r in self.rows if len(r) >= 9 and r[2].isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_passes(rank, step, batch):
+    from nzcb_circom_b200 import nzcp_helpers as H
+    out = []
+    for i in range(batch):
+        p = H.synth_pass(100000 * rank + 1000 * step + i)
+        out.append((p["toBeSigned"], p["data"]))
+    return out
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the CPU stand-in for `circom WASM witness + snarkjs plonk.prove`, all host threads."""
+    if rank != 0:
+        return 0
+    try:
+        from nzcb_circom_b200 import Context
+        from nzcb_circom_b200.prover import NzcpProver, default_tau
+        from oracle import c_oracle as C
+    except Exception as e:  # pragma: no cover
+        print(json.dumps({"impl": "reference", "unavailable": f"cannot load the oracle port: {e}"}))
+        return 0
+    # key material is prepared once with the GPU `plonk setup` (preparation, untimed); the timed path is CPU only
+    pr = NzcpProver(live=True, tau=default_tau(), ctx=Context(int(os.environ.get("LOCAL_RANK", "0"))))
+    zkey = pr.setup(keep_zkey=True)
+    cores = C.num_threads()
+    steps = args.steps if args.steps is not None else 2
+    warm = args.warmup if args.warmup is not None else 1
+    wprog = pr.art.wprog_bytes()
+    times = []
+    for s in range(warm + steps):
+        inp = pr.marshal_passes(make_passes(0, s, 1))
+        bl = list(range(1, 10))
+        t = time.perf_counter()
+        rc, proof, pub = C.fullprove(wprog, inp, zkey, bl, 3)
+        dt = time.perf_counter() - t
+        assert rc == 0, rc
+        if s >= warm:
+            times.append(dt)
+    total = sum(times)
+    value = steps / total
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warm, "ms_per_step": 1000 * total / steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64x4 (256-bit Montgomery, integer)", "data": "synthetic",
+            "config": {"workload": "nzcp_live fullProve (witness program + PLONK prove), domain 2^21, 1 pass per step",
+                       "domain_log2": 21, "note": "CPU port of the oracle (C, OpenMP); snarkjs/Node cannot run in this image"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{steps} whole nzcp_live proofs (witness + prove), one per step"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--batch", type=int, default=2, help="passes per GPU per step")
+    ap.add_argument("--impl", default="nzcb")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank, local_rank, world = _rank_env()
+
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    steps = args.steps if args.steps is not None else 5
+    warm = args.warmup if args.warmup is not None else 3
+    warm = max(warm, 3)
+    B = args.batch
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+        torch.cuda.set_device(local_rank)
+        dist_mod.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+        dist = dist_mod
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    from nzcb_circom_b200 import Context
+    from nzcb_circom_b200.prover import NzcpProver, default_tau
+
+    ctx = Context(local_rank)
+    pr = NzcpProver(live=True, tau=default_tau(), ctx=ctx)
+    want_cpu = (rank == 0 and world == 1 and not args.no_cpu_baseline)
+    zkey = pr.setup(keep_zkey=want_cpu)
+    n_in = pr.art.n_in
+
+    # integer-pipe peak, measured live on this GPU (IMAD32 / s)
+    imad_peak = ctx.microbench(0, 4000, 8) if rank == 0 else 0.0
+
+    # ---- inputs: synthetic passes for every step, marshalled up front for the device-resident leg
+    all_passes = [make_passes(rank, s, B) for s in range(warm + steps)]
+    marshalled = [pr.marshal_passes(p) for p in all_passes]
+    dptrs = []
+    for m in marshalled:
+        d = ctx.dev_alloc(len(m))
+        ctx.dev_upload(d, m)
+        dptrs.append(d)
+
+    def check(res):
+        for proof, _pub, st in res:
+            if st != 0 or proof is None:
+                raise RuntimeError(f"proof failed with status {st}")
+
+    # ---- leg 1: device-resident throughput (value)
+    for s in range(warm):
+        check(pr.prove_raw(None, B, None, device_inputs=dptrs[s]))
+    sampler = ClockSampler(local_rank)
+    barrier()
+    ctx.profile(True)
+    launches0 = ctx.launches
+    sampler.start()
+    dev_ms = 0.0
+    t0 = time.perf_counter()
+    for s in range(warm, warm + steps):
+        check(pr.prove_raw(None, B, None, device_inputs=dptrs[s]))
+        dev_ms += ctx.last_device_ms
+    wall_dev = time.perf_counter() - t0
+    clocks = sampler.stop()
+    n_launch, acc_ms, acc_modmul = ctx.profile_read()
+    ctx.profile(False)
+    gpu_launches = ctx.launches - launches0
+    barrier()
+    dev_s = max_over_ranks(dev_ms / 1000.0)
+    value = world * steps * B / dev_s
+
+    # ---- leg 2: end to end through the public API with host buffers
+    for s in range(min(warm, 1)):
+        check(pr.prove_passes(all_passes[s]))
+    barrier()
+    t0 = time.perf_counter()
+    last = None
+    for s in range(warm, warm + steps):
+        last = pr.prove_passes(all_passes[s])  # marshal + H2D + witness + prove + D2H
+        check(last)
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e = world * steps * B / e2e_s
+
+    # ---- single-proof latency (B = 1), device-resident
+    one = pr.marshal_passes(all_passes[0][:1])
+    t0 = time.perf_counter()
+    check(pr.prove_raw(one, 1))
+    latency_ms = 1000 * (time.perf_counter() - t0)
+
+    if rank != 0:
+        return 0
+
+    # ---- roofline of the dominant kernel
+    achieved = acc_modmul * 264.0 / (acc_ms / 1000.0) if acc_ms > 0 else 0.0
+    hbm_peak = None
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            hbm_peak = json.load(f).get("hbm_gbs")
+    except Exception:
+        pass
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_msm_accum_ncu.json")) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"bound": "imad", "kernel": "k_msm_accum (MSM bucket accumulation)", "achieved": achieved / 1e12,
+                "peak": imad_peak / 1e12, "unit": "TIMAD32/s", "frac": achieved / imad_peak if imad_peak else None,
+                "traffic": traffic, "launches": n_launch, "avg_launch_ms": acc_ms / n_launch if n_launch else None,
+                "kernel_share_of_step": acc_ms / (dev_ms) if dev_ms else None,
+                "peak_source": "measured live: nzcb_microbench kind 0 (IMAD), this GPU; MEASURED_PEAKS.json has no integer-pipe figure",
+                "hbm_gbs_measured_peak": hbm_peak}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
+            "ms_per_step": 1000 * dev_s / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32x8 (256-bit Montgomery, integer)", "data": "synthetic",
+            "config": {"workload": "nzcp_live fullProve (witness program + PLONK prove), BASELINE.json configs[1] x batch",
+                       "batch_per_gpu": B, "domain_log2": 21, "n_constraints_r1cs": pr.art.n_constraints,
+                       "parallelism": f"independent proofs sharded over {world} GPU(s), no collective",
+                       "l2": "inputs larger than L2: each proof streams the 3 GiB resident zkey plus ~2.5 GiB of scratch"},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": B * n_in * 32, "d2h_bytes_per_step": B * (800 + 96 + 4)},
+            "gpu_launches": int(gpu_launches), "clocks": clocks, "roofline": roofline,
+            "latency_ms_single_proof": latency_ms, "wall_s_device_leg": wall_dev,
+            "setup_s": pr.timings}
+
+    if want_cpu:
+        try:
+            from oracle import c_oracle as C
+            inp = pr.marshal_passes(all_passes[0][:1])
+            t0 = time.perf_counter()
+            rc, cproof, _ = C.fullprove(pr.art.wprog_bytes(), inp, zkey, list(range(1, 10)), 3)
+            dt = time.perf_counter() - t0
+            gproof = pr.prove_raw(inp, 1, [list(range(1, 10))])[0][0]
+            line["cpu_baseline"] = {"value": 1.0 / dt, "unit": UNIT, "cores": C.num_threads(), "kind": "port",
+                                    "sample": "1 whole nzcp_live proof (witness + prove) of the same workload",
+                                    "proof_bytes_equal_gpu": bool(rc == 0 and cproof == gproof)}
+        except Exception as e:  # the baseline is reported, never the product
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": None, "kind": "port", "sample": f"failed: {e}"}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -142,6 +142,18 @@ int32_t nzcb_plonk_fullprove_batch(nzcb_ctx* ctx, const nzcb_circuit* c, const n
                                    size_t B, const uint8_t* blinders_le /* B x 9 x 32 or NULL */, nzcb_proof* out,
                                    uint8_t* public_le /* B x nPublic x 32 */, int32_t* status /* B */);
 
+/* same with the marshalled inputs already resident in HBM (buffer from nzcb_dev_alloc / nzcb_dev_upload):
+ * the device-resident throughput figure of bench.py */
+int32_t nzcb_plonk_fullprove_batch_dev(nzcb_ctx* ctx, const nzcb_circuit* c, const nzcb_zkey* zk,
+                                       const void* d_inputs_le, size_t B, const uint8_t* blinders_le, nzcb_proof* out,
+                                       uint8_t* public_le, int32_t* status);
+
+/* CUDA-event timing of the dominant kernel (MSM bucket accumulation) on the ctx stream.
+ * nzcb_profile(ctx, 1) starts collecting; nzcb_profile_read returns launches, summed device ms and the
+ * algorithmic modmul count of those launches (160 per MSM point) and resets. */
+int32_t nzcb_profile(nzcb_ctx* ctx, int32_t enable);
+int32_t nzcb_profile_read(nzcb_ctx* ctx, uint64_t* launches, double* total_ms, double* alg_modmul);
+
 #ifdef __cplusplus
 }
 #endif

@@ -68,6 +68,10 @@ SIGNATURES = {
     "nzcb_circuit_info": (_i32, [_vp] + [ctypes.POINTER(_u32)] * 3),
     "nzcb_witness_batch": (_i32, [_vp, _vp, _vp, _sz, _vp, _vp]),
     "nzcb_plonk_fullprove_batch": (_i32, [_vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp]),
+    "nzcb_plonk_fullprove_batch_dev": (_i32, [_vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp]),
+    "nzcb_profile": (_i32, [_vp, _i32]),
+    "nzcb_profile_read": (_i32, [_vp, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_double),
+                                 ctypes.POINTER(ctypes.c_double)]),
 }
 
 
@@ -126,6 +130,15 @@ class Context:
         v = ctypes.c_double()
         self.check(self.lib.nzcb_microbench(self.h, kind, iters, blocks_per_sm, ctypes.byref(v)))
         return v.value
+
+    def profile(self, enable=True):
+        self.check(self.lib.nzcb_profile(self.h, 1 if enable else 0))
+
+    def profile_read(self):
+        """(launches, total device ms, algorithmic modmul) of the MSM bucket-accumulation kernel"""
+        n, ms, mm = ctypes.c_uint64(), ctypes.c_double(), ctypes.c_double()
+        self.check(self.lib.nzcb_profile_read(self.h, ctypes.byref(n), ctypes.byref(ms), ctypes.byref(mm)))
+        return n.value, ms.value, mm.value
 
     def selftest_mul(self, n=1 << 20):
         v = ctypes.c_uint64()

@@ -53,10 +53,39 @@ extern "C" void nzcb_ctx_free(nzcb_ctx* ctx) {
     for (auto& kv : ctx->twiddles) cudaFree(kv.second);
     for (auto& kv : ctx->scratch)
         if (kv.second.first) cudaFree(kv.second.first);
+    for (auto& e : ctx->prof_ev) {
+        cudaEventDestroy(e.first);
+        cudaEventDestroy(e.second);
+    }
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
+}
+
+extern "C" int32_t nzcb_profile(nzcb_ctx* ctx, int32_t enable) {
+    if (!ctx) return NZCB_E_INVALID;
+    NZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->prof_on = enable != 0;
+    ctx->prof_used = 0;
+    ctx->prof_modmul = 0;
+    return 0;
+}
+extern "C" int32_t nzcb_profile_read(nzcb_ctx* ctx, uint64_t* launches, double* total_ms, double* alg_modmul) {
+    if (!ctx) return NZCB_E_INVALID;
+    NZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    double ms = 0;
+    for (size_t i = 0; i < ctx->prof_used; i++) {
+        float t = 0;
+        cudaEventElapsedTime(&t, ctx->prof_ev[i].first, ctx->prof_ev[i].second);
+        ms += t;
+    }
+    if (launches) *launches = ctx->prof_used;
+    if (total_ms) *total_ms = ms;
+    if (alg_modmul) *alg_modmul = ctx->prof_modmul;
+    ctx->prof_used = 0;
+    ctx->prof_modmul = 0;
+    return 0;
 }
 
 extern "C" const char* nzcb_last_error(const nzcb_ctx* ctx) { return ctx ? ctx->err : g_noctx_err; }

@@ -25,6 +25,11 @@ struct nzcb_ctx {
     float last_ms = 0.f;
     uint64_t launches = 0;
     char err[512] = {0};
+    // optional CUDA-event timing of the dominant kernel (k_msm_accum) for bench.py's roofline
+    bool prof_on = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_ev;
+    size_t prof_used = 0;
+    double prof_modmul = 0;  // algorithmic modmul of the timed launches (160 per MSM point)
     // twiddle tables per (log_n, inverse)
     std::map<uint32_t, nzcb::Fr*> twiddles;
     // grow-only scratch arenas keyed by name, so steady-state proving never mallocs

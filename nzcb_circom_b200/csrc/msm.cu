@@ -236,7 +236,21 @@ int msm_dev(nzcb_ctx* ctx, const G1Affine* d_bases, const uint32_t* d_scalars, s
     NZ_LAUNCH(ctx, k_scan_excl, 1, 1024, 0, counts, offsets, p.nb);
     NZ_LAUNCH(ctx, k_msm_scatter, div_up(n, 256), 256, 0, d_scalars, n, mont ? 1 : 0, p.c, p.W, p.nbw, offsets, cursor,
               sorted);
+    if (ctx->prof_on) {
+        if (ctx->prof_used == ctx->prof_ev.size()) {
+            cudaEvent_t a, b;
+            NZ_CUDA(ctx, cudaEventCreate(&a));
+            NZ_CUDA(ctx, cudaEventCreate(&b));
+            ctx->prof_ev.push_back({a, b});
+        }
+        NZ_CUDA(ctx, cudaEventRecord(ctx->prof_ev[ctx->prof_used].first, ctx->stream));
+    }
     NZ_LAUNCH(ctx, k_msm_accum, div_up(p.nb, 128), 128, 0, d_bases, sorted, offsets, p.nb, buckets);
+    if (ctx->prof_on) {
+        NZ_CUDA(ctx, cudaEventRecord(ctx->prof_ev[ctx->prof_used].second, ctx->stream));
+        ctx->prof_used++;
+        ctx->prof_modmul += 160.0 * (double)n;
+    }
     NZ_LAUNCH(ctx, k_msm_reduce1, div_up((size_t)p.W * p.C, 128), 128, 0, buckets, p.W, p.nbw, p.C, p.S, run, acc);
     NZ_LAUNCH(ctx, k_msm_reduce2, p.W, p.C, p.C * sizeof(G1XYZZ), run, acc, p.C, p.log_C, p.log_S, win);
     NZ_LAUNCH(ctx, k_msm_final, 1, 32, 0, win, p.W, p.c, d_out);

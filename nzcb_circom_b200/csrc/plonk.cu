@@ -906,9 +906,24 @@ uint32_t circuit_n_in(const nzcb_circuit* c);
 }  // namespace nzcb
 
 // snarkjs plonk.fullProve: witness program on the GPU, the wires never leave HBM, then the prover
+static int32_t fullprove_impl(nzcb_ctx* ctx, const nzcb_circuit* cir, const nzcb_zkey* zk, const uint8_t* inputs_le,
+                              bool inputs_on_device, size_t B, const uint8_t* blinders_le, nzcb_proof* out,
+                              uint8_t* public_le, int32_t* status);
+
 extern "C" int32_t nzcb_plonk_fullprove_batch(nzcb_ctx* ctx, const nzcb_circuit* cir, const nzcb_zkey* zk,
                                               const uint8_t* inputs_le, size_t B, const uint8_t* blinders_le,
                                               nzcb_proof* out, uint8_t* public_le, int32_t* status) {
+    return fullprove_impl(ctx, cir, zk, inputs_le, false, B, blinders_le, out, public_le, status);
+}
+extern "C" int32_t nzcb_plonk_fullprove_batch_dev(nzcb_ctx* ctx, const nzcb_circuit* cir, const nzcb_zkey* zk,
+                                                  const void* d_inputs_le, size_t B, const uint8_t* blinders_le,
+                                                  nzcb_proof* out, uint8_t* public_le, int32_t* status) {
+    return fullprove_impl(ctx, cir, zk, (const uint8_t*)d_inputs_le, true, B, blinders_le, out, public_le, status);
+}
+
+static int32_t fullprove_impl(nzcb_ctx* ctx, const nzcb_circuit* cir, const nzcb_zkey* zk, const uint8_t* inputs_le,
+                              bool inputs_on_device, size_t B, const uint8_t* blinders_le, nzcb_proof* out,
+                              uint8_t* public_le, int32_t* status) {
     if (!ctx || !cir || !zk || !out || !status || (!inputs_le && circuit_n_in(cir))) return NZCB_E_INVALID;
     if (zk->ctx != ctx) return ctx->fail(NZCB_E_INVALID, "zkey was loaded on a different context");
     const uint32_t n_w = zk->n_vars - zk->n_add;
@@ -928,10 +943,12 @@ extern "C" int32_t nzcb_plonk_fullprove_batch(nzcb_ctx* ctx, const nzcb_circuit*
     cudaEventRecord(ctx->ev0, ctx->stream);
     for (size_t done = 0; done < B; done += chunk) {
         const size_t nb = std::min(chunk, B - done);
-        if (n_in)
+        const Fr* cur_in = d_in;
+        if (inputs_on_device) cur_in = (const Fr*)inputs_le + done * n_in;
+        else if (n_in)
             NZ_CUDA(ctx, cudaMemcpyAsync(d_in, inputs_le + done * n_in * 32, nb * n_in * 32, cudaMemcpyHostToDevice,
                                          ctx->stream));
-        NZ_TRY(witness_dev(ctx, cir, d_in, nb, d_w, d_st));
+        NZ_TRY(witness_dev(ctx, cir, cur_in, nb, d_w, d_st));
         NZ_CUDA(ctx, cudaMemcpyAsync(status + done, d_st, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
         NZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         for (size_t i = 0; i < nb; i++) {

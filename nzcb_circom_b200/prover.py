@@ -67,8 +67,9 @@ class CircuitProver:
         """inputs: list of circuit input dicts -> [(proof bytes | None, publicSignals, status)]"""
         return plonk.fullProveBatch(inputs, self.tester, self.zk, blinders_list, self.ctx)
 
-    def prove_raw(self, inputs_le, B, blinders_list=None):
-        return plonk.fullProveRaw(inputs_le, B, self.tester._handle(self.ctx), self.zk, blinders_list, self.ctx)
+    def prove_raw(self, inputs_le, B, blinders_list=None, device_inputs=None):
+        return plonk.fullProveRaw(inputs_le, B, self.tester._handle(self.ctx), self.zk, blinders_list, self.ctx,
+                                  device_inputs)
 
     def marshal(self, inputs):
         """host-side marshalling of input dicts to the B x nInputs x 32 B buffer the C ABI takes"""

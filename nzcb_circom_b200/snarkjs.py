@@ -202,10 +202,12 @@ class _Plonk:
             flat += b"".join(int(v).to_bytes(32, "little") for v in vals)
         return self.fullProveRaw(bytes(flat), len(inputs), h, zk, blinders_list, ctx)
 
-    def fullProveRaw(self, inputs_le, B, circuit_handle, zk, blinders_list=None, ctx=None):
-        """inputs already marshalled: B x nInputs x 32 B canonical LE"""
+    def fullProveRaw(self, inputs_le, B, circuit_handle, zk, blinders_list=None, ctx=None, device_inputs=None):
+        """inputs already marshalled: B x nInputs x 32 B canonical LE (host bytes), or
+        device_inputs = a device pointer holding the same bytes (nzcb_dev_upload)"""
         ctx = ctx or zk.ctx
-        ibuf = (ctypes.c_uint8 * max(1, len(inputs_le))).from_buffer_copy(inputs_le or b"\0")
+        ibuf = as_cbuf(inputs_le or b"\0") if device_inputs is None else device_inputs
+        fn = ctx.lib.nzcb_plonk_fullprove_batch if device_inputs is None else ctx.lib.nzcb_plonk_fullprove_batch_dev
         bl = None
         if blinders_list is not None:
             raw = b"".join(int(x).to_bytes(32, "little") for bs in blinders_list for x in bs)
@@ -214,7 +216,7 @@ class _Plonk:
         npub = max(1, zk.n_public)
         pub = (ctypes.c_uint8 * (32 * npub * B))()
         status = (ctypes.c_int32 * B)()
-        ctx.check(ctx.lib.nzcb_plonk_fullprove_batch(ctx.h, circuit_handle, zk.h, ibuf, B, bl, out, pub, status))
+        ctx.check(fn(ctx.h, circuit_handle, zk.h, ibuf, B, bl, out, pub, status))
         res = []
         for i in range(B):
             pb = bytes(pub[i * 32 * zk.n_public:(i + 1) * 32 * zk.n_public])
