@@ -89,6 +89,20 @@ int32_t nzcb_ntt_fr_dev(nzcb_ctx* ctx, void* d_data_lem, uint32_t log_n, int32_t
 int32_t nzcb_msm_g1_dev(nzcb_ctx* ctx, const void* d_bases_affine_lem, const void* d_scalars_le, size_t n,
                         uint8_t out_affine_lem[64]);
 
+/* Fixed bases (the way the prover holds the zkey's SRS): the window shifts 2^(c w) P_i are precomputed once,
+ * every MSM over the table then uses one bucket set and 13 digits per scalar at 2^21 points.
+ * bases: n x 64 B affine LEM (host).  The table owns ~(254/c + 1) x n x 64 B of HBM. */
+typedef struct nzcb_g1_table nzcb_g1_table;
+int32_t nzcb_g1_table_create(nzcb_ctx* ctx, const uint8_t* bases_affine_lem, size_t n, nzcb_g1_table** out);
+void nzcb_g1_table_free(nzcb_g1_table* t);
+/* sum_i scalars[i] * bases[i] over the first n bases of the table; scalars n x 32 B LE (host) */
+int32_t nzcb_msm_g1_table(nzcb_ctx* ctx, const nzcb_g1_table* t, const uint8_t* scalars_le, size_t n,
+                          uint8_t out_affine_lem[64]);
+/* K <= 4 MSMs over the same table as one batch (one sort, one accumulation launch, one reduction);
+ * d_scalars[k] = device buffer of n[k] x 32 B LE; out = K x 64 B affine LEM (host) */
+int32_t nzcb_msm_g1_table_dev(nzcb_ctx* ctx, const nzcb_g1_table* t, const void* const* d_scalars, const size_t* n,
+                              int32_t K, uint8_t* out_affine_lem);
+
 /* ---- SRS + setup: `snarkjs powersoftau new` / `plonk setup` roles --------- */
 /* [tau^i]G1, i < count, affine LEM (insecure known-trapdoor SRS, Makefile:64-67 role) */
 int32_t nzcb_srs_g1(nzcb_ctx* ctx, const uint8_t tau_le[32], size_t count, uint8_t* out_affine_lem);

@@ -69,6 +69,10 @@ SIGNATURES = {
     "nzcb_witness_batch": (_i32, [_vp, _vp, _vp, _sz, _vp, _vp]),
     "nzcb_plonk_fullprove_batch": (_i32, [_vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp]),
     "nzcb_plonk_fullprove_batch_dev": (_i32, [_vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp]),
+    "nzcb_g1_table_create": (_i32, [_vp, _vp, _sz, ctypes.POINTER(_vp)]),
+    "nzcb_g1_table_free": (None, [_vp]),
+    "nzcb_msm_g1_table": (_i32, [_vp, _vp, _vp, _sz, _vp]),
+    "nzcb_msm_g1_table_dev": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp]),
     "nzcb_profile": (_i32, [_vp, _i32]),
     "nzcb_profile_read": (_i32, [_vp, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_double),
                                  ctypes.POINTER(ctypes.c_double)]),

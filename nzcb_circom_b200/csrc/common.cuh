@@ -96,9 +96,21 @@ static inline unsigned div_up(size_t a, size_t b) { return (unsigned)((a + b - 1
 // --- internal device-level entry points (all asynchronous on ctx->stream) ---
 // ntt.cu
 int ntt_dev(nzcb_ctx* ctx, Fr* d_data, uint32_t log_n, bool inverse);
-// msm.cu : result left in d_out (one G1XYZZ) ; scalars 8 x u32 each
+// msm.cu : result left in d_out (one G1XYZZ) ; scalars 8 x u32 each.  One-shot bases (window mode).
 int msm_dev(nzcb_ctx* ctx, const G1Affine* d_bases, const uint32_t* d_scalars, size_t n, bool scalars_mont,
             G1XYZZ* d_out);
-int msm_to_host_affine(nzcb_ctx* ctx, const G1XYZZ* d_pt, G1Affine* h_out);
+// fixed bases with the window shifts precomputed: pts[w * stride + i] = 2^(c w) P_i, w < W
+struct G1Table {
+    G1Affine* pts = nullptr;
+    size_t n = 0, stride = 0;
+    uint32_t c = 0, W = 0;
+};
+int g1_table_build(nzcb_ctx* ctx, const G1Affine* d_bases, size_t n, G1Table* out);
+void g1_table_free(G1Table* t);
+// K <= 4 MSMs over the first n[k] bases of one table as a single batch; results in d_out[0..K)
+int msm_table_dev(nzcb_ctx* ctx, const G1Table& tab, const uint32_t* const* d_scalars, const size_t* n, int K,
+                  bool scalars_mont, G1XYZZ* d_out);
+// D2H + stream sync + affine conversion of `count` <= 4 results
+int msm_to_host_affine(nzcb_ctx* ctx, const G1XYZZ* d_pt, G1Affine* h_out, int count = 1);
 
 }  // namespace nzcb

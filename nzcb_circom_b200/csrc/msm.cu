@@ -2,55 +2,81 @@
 // G1.multiExpAffine (un-vendored, /root/reference/yarn.lock:3905; called nine
 // times per proof by snarkjs plonk.prove).
 //
-// Pippenger with signed c-bit digits (buckets 1..2^(c-1), negative digits add
-// the negated base):
-//   1. k_msm_count    one thread per scalar: recode, histogram the (window,|digit|) keys
-//   2. k_scan_excl    bucket offsets
-//   3. k_msm_scatter  counting-sort the point indices by bucket (order inside a
-//                     bucket is arbitrary -- the group sum is the same element)
-//   4. k_msm_accum    one thread per bucket: XYZZ += affine over its run (8M+2S each)
-//   5. k_msm_reduce1  per (window, chunk of S buckets): running-sum trick
-//      k_msm_reduce2  per window: block tree reductions combine the chunks
-//      k_msm_final    Horner over windows
-// Algorithmic work: n * windows * 10 modmul in step 4.
+// Pippenger with signed c-bit digits (buckets 1..2^(c-1); a negative digit adds
+// the negated base; scalars above (r-1)/2 are replaced by r - s with the sign
+// flipped, so small negative wire values cost as little as small positive ones).
+//
+// Two bucket layouts:
+//   table mode   (fixed bases, the zkey's SRS): the bases come with the window
+//                shifts 2^(c w) P_i precomputed once (G1Table), so every window
+//                feeds ONE bucket set per MSM and there is no per-window Horner;
+//                c = 20 -> 13 digits per scalar instead of 16.
+//   window mode  (one-shot bases, nzcb_msm_g1): one bucket set per window, Horner
+//                over the windows at the end.
+// Several MSMs over the same bases (A/B/C, T1/T2/T3, Wxi/Wxiw) run as one batch of
+// "jobs": one sort, one accumulation launch, one reduction.
+//
+//   1. k_msm_digits<COUNT>   recode, histogram the bucket keys
+//   2. scan_excl             bucket offsets (multi-block)
+//   3. k_msm_digits<SCATTER> counting-sort the point references by bucket
+//   4. k_msm_accum           THE hot kernel.  Equal-length segments of the sorted
+//                            list per thread (perfect balance whatever the bucket
+//                            sizes): XYZZ += affine (8M + 2S) along the segment;
+//                            buckets inside a segment are written directly, the
+//                            first / last (possibly shared with the neighbours) go
+//                            to a (key, partial) list
+//      k_seg_level           segmented reduction of that list, level by level
+//   5. k_bred                sum_b (b+1) B_b by chunked running sums, recursively
+//      k_msm_finish          window mode: Horner over the windows
+// Algorithmic work: n * 16 * 10 modmul in step 4.
 #include "common.cuh"
 #include <stdlib.h>
+#include <algorithm>
 
 namespace nzcb {
 
+constexpr uint32_t KEY_NONE = 0xffffffffu;
+
 struct MsmPlan {
-    uint32_t c;        // window bits
-    uint32_t W;        // number of windows
-    uint32_t nbw;      // buckets per window = 2^(c-1)
-    uint32_t C;        // chunks per window in the reduction
-    uint32_t S;        // buckets per chunk
-    uint32_t log_S;
-    uint32_t log_C;
-    size_t nb;         // total buckets
+    uint32_t c;      // window bits
+    uint32_t W;      // digits per scalar
+    uint32_t nbw;    // buckets per set = 2^(c-1)
+    uint32_t G;      // bucket sets: K (table mode) or K * W (window mode)
+    bool unified;    // table mode
+    uint32_t stride; // table row stride (points)
 };
 
-static MsmPlan make_plan(size_t n) {
+static uint32_t floor_log2(size_t n) {
     uint32_t lg = 0;
     while (((size_t)2 << lg) <= n) lg++;
-    int c = (int)lg - 5;
-    if (c < 4) c = 4;
-    if (c > 16) c = 16;
-    const char* env = getenv("NZCB_MSM_WINDOW");
+    return lg;
+}
+
+static uint32_t env_window(uint32_t c, const char* name, uint32_t hi) {
+    const char* env = getenv(name);
     if (env) {
         int v = atoi(env);
-        if (v >= 2 && v <= 20) c = v;
+        if (v >= 2 && v <= (int)hi) c = (uint32_t)v;
     }
+    return c;
+}
+
+uint32_t msm_table_window(size_t n) {
+    int c = (int)floor_log2(n ? n : 1) - 1;
+    c = std::max(4, std::min(20, c));
+    return env_window((uint32_t)c, "NZCB_MSM_TABLE_WINDOW", 22);
+}
+
+static MsmPlan make_plan_window(size_t n, int K) {
+    int c = (int)floor_log2(n ? n : 1) - 5;
+    c = std::max(4, std::min(16, c));
     MsmPlan p;
-    p.c = (uint32_t)c;
+    p.c = env_window((uint32_t)c, "NZCB_MSM_WINDOW", 20);
     p.W = 254 / p.c + 1;
     p.nbw = 1u << (p.c - 1);
-    p.C = p.nbw < 256 ? p.nbw : 256;
-    p.S = p.nbw / p.C;
-    p.log_S = 0;
-    while ((1u << p.log_S) < p.S) p.log_S++;
-    p.log_C = 0;
-    while ((1u << p.log_C) < p.C) p.log_C++;
-    p.nb = (size_t)p.W * p.nbw;
+    p.G = (uint32_t)K * p.W;
+    p.unified = false;
+    p.stride = 0;
     return p;
 }
 
@@ -62,180 +88,380 @@ __device__ __forceinline__ uint32_t get_bits(const uint32_t* s, uint32_t off, ui
     return v & ((1u << c) - 1);
 }
 
-// Signed-digit recode of one scalar; calls f(window, bucket_index, negative) per non-zero digit.
+constexpr int NZ_MSM_MAXJOBS = 4;
+struct DigitArgs {
+    const uint32_t* scalars[NZ_MSM_MAXJOBS];
+    uint32_t n[NZ_MSM_MAXJOBS];
+    uint32_t mont[NZ_MSM_MAXJOBS];
+    uint32_t c, W, nbw, unified, stride;
+};
+
+// s > (r - 1) / 2 ?
+__device__ __forceinline__ bool above_half(const Fr& s) {
+    constexpr uint32_t H[8] = {0xf8000000u, 0xa1f0fac9u, 0x3cdcb848u, 0x9419f424u,
+                               0x40c0ac2eu, 0xdc2822dbu, 0x7098d014u, 0x18322739u};
+#pragma unroll
+    for (int i = 7; i >= 0; i--) {
+        if (s.v[i] > H[i]) return true;
+        if (s.v[i] < H[i]) return false;
+    }
+    return false;
+}
+
+// Signed-digit recode of scalar i of job k; calls f(bucket key, point reference | sign << 31) per non-zero digit.
 template <class F>
-__device__ __forceinline__ void for_each_digit(const uint32_t* __restrict__ scalars, size_t i, bool mont, uint32_t c,
-                                               uint32_t W, F f) {
-    Fr s = reinterpret_cast<const Fr*>(scalars)[i];
-    if (mont) s = s.from_mont();
+__device__ __forceinline__ void for_each_digit(const DigitArgs& a, uint32_t k, uint32_t i, F f) {
+    Fr s = reinterpret_cast<const Fr*>(a.scalars[k])[i];
+    if (a.mont[k]) {
+        s = s.from_mont();
+    } else {
+        // multiExpAffine takes plain 256-bit integers: s * P = (s mod r) * P, and 2^256 < 6 r
+        for (int it = 0; it < 5; it++) s = Fr::reduce_once(s);
+    }
+    if (s.is_zero()) return;
+    const bool neg = above_half(s);
+    if (neg) s = Fr::modulus() - s;
     uint32_t carry = 0;
-    const uint32_t half = 1u << (c - 1);
-    for (uint32_t w = 0; w < W; w++) {
-        uint32_t d = get_bits(s.v, w * c, c) + carry;
+    const uint32_t half = 1u << (a.c - 1);
+    for (uint32_t w = 0; w < a.W; w++) {
+        uint32_t d = get_bits(s.v, w * a.c, a.c) + carry;
+        bool dneg = false;
         if (d > half) {
             carry = 1;
-            const uint32_t mag = (1u << c) - d;  // |d - 2^c|; 0 when d == 2^c (digit 0, carry 1)
-            if (mag) f(w, mag - 1, true);
+            d = (1u << a.c) - d;  // |d - 2^c|; 0 when d == 2^c (digit 0, carry 1)
+            dneg = true;
         } else {
             carry = 0;
-            if (d) f(w, d - 1, false);
+        }
+        if (d) {
+            const uint32_t set = a.unified ? k : k * a.W + w;
+            const uint32_t ref = a.unified ? w * a.stride + i : i;
+            f(set * a.nbw + (d - 1), ref | ((neg != dneg) ? 0x80000000u : 0u));
         }
     }
 }
 
-__global__ void k_msm_count(const uint32_t* __restrict__ scalars, size_t n, int mont, uint32_t c, uint32_t W,
-                            uint32_t nbw, uint32_t* __restrict__ counts) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    for_each_digit(scalars, i, mont != 0, c, W,
-                   [&](uint32_t w, uint32_t b, bool) { atomicAdd(&counts[(size_t)w * nbw + b], 1u); });
+// COUNT: histogram into cnt.   !COUNT: scatter, cnt is the per-bucket cursor (zeroed), offsets the scan.
+template <bool COUNT>
+__global__ void __launch_bounds__(256) k_msm_digits(DigitArgs a, uint32_t* __restrict__ cnt,
+                                                    const uint32_t* __restrict__ offsets, uint32_t* __restrict__ sorted) {
+    const uint32_t k = blockIdx.y;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n[k]) return;
+    for_each_digit(a, k, i, [&](uint32_t key, uint32_t ref) {
+        if (COUNT) {
+            atomicAdd(&cnt[key], 1u);
+        } else {
+            const uint32_t pos = atomicAdd(&cnt[key], 1u);
+            sorted[offsets[key] + pos] = ref;
+        }
+    });
 }
 
-// exclusive scan of `n` counts into offsets[0..n] (offsets[n] = total); single block
-__global__ void __launch_bounds__(1024) k_scan_excl(const uint32_t* __restrict__ counts, uint32_t* __restrict__ offsets,
-                                                    size_t n) {
+// ---- exclusive scan of n u32 counts into offsets[0..n], offsets[n] = total ------------------
+constexpr uint32_t SCAN_ITEMS = 8, SCAN_THREADS = 256, SCAN_TILE = SCAN_ITEMS * SCAN_THREADS;
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_tile(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
+                                                            uint32_t* __restrict__ tile_sums, size_t n) {
+    __shared__ uint32_t part[SCAN_THREADS];
+    const uint32_t t = threadIdx.x;
+    const size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)t * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS], sum = 0;
+#pragma unroll
+    for (uint32_t j = 0; j < SCAN_ITEMS; j++) {
+        v[j] = base + j < n ? in[base + j] : 0u;
+        sum += v[j];
+    }
+    part[t] = sum;
+    __syncthreads();
+    for (uint32_t off = 1; off < SCAN_THREADS; off <<= 1) {
+        const uint32_t x = t >= off ? part[t - off] : 0u;
+        __syncthreads();
+        part[t] += x;
+        __syncthreads();
+    }
+    uint32_t run = part[t] - sum;
+#pragma unroll
+    for (uint32_t j = 0; j < SCAN_ITEMS; j++) {
+        if (base + j < n) out[base + j] = run;
+        run += v[j];
+    }
+    if (t == SCAN_THREADS - 1) tile_sums[blockIdx.x] = part[t];
+}
+// single block: exclusive scan of the tile sums in place; writes the grand total to *total
+__global__ void __launch_bounds__(1024) k_scan_tops(uint32_t* __restrict__ sums, size_t n, uint32_t* __restrict__ total) {
     __shared__ uint32_t part[1024];
     const uint32_t t = threadIdx.x;
     const size_t per = (n + 1023) / 1024;
-    const size_t lo = (size_t)t * per;
-    const size_t hi = lo + per < n ? lo + per : n;
+    const size_t lo = (size_t)t * per, hi = lo + per < n ? lo + per : n;
     uint32_t sum = 0;
-    for (size_t k = lo; k < hi; k++) sum += counts[k];
+    for (size_t k = lo; k < hi; k++) sum += sums[k];
     part[t] = sum;
     __syncthreads();
     for (uint32_t off = 1; off < 1024; off <<= 1) {
-        uint32_t v = t >= off ? part[t - off] : 0;
+        const uint32_t x = t >= off ? part[t - off] : 0u;
         __syncthreads();
-        part[t] += v;
+        part[t] += x;
         __syncthreads();
     }
     uint32_t run = part[t] - sum;
     for (size_t k = lo; k < hi; k++) {
-        offsets[k] = run;
-        run += counts[k];
+        const uint32_t c = sums[k];
+        sums[k] = run;
+        run += c;
     }
-    if (t == 1023) offsets[n] = part[1023];
+    if (t == 1023) *total = part[1023];
+}
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_add(uint32_t* __restrict__ out, const uint32_t* __restrict__ tile_offs,
+                                                           size_t n) {
+    const size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
+    const uint32_t add = tile_offs[blockIdx.x];
+#pragma unroll
+    for (uint32_t j = 0; j < SCAN_ITEMS; j++)
+        if (base + j < n) out[base + j] += add;
 }
 
-__global__ void k_msm_scatter(const uint32_t* __restrict__ scalars, size_t n, int mont, uint32_t c, uint32_t W,
-                              uint32_t nbw, const uint32_t* __restrict__ offsets, uint32_t* __restrict__ cursor,
-                              uint32_t* __restrict__ sorted) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    for_each_digit(scalars, i, mont != 0, c, W, [&](uint32_t w, uint32_t b, bool neg) {
-        const size_t key = (size_t)w * nbw + b;
-        const uint32_t pos = atomicAdd(&cursor[key], 1u);
-        sorted[(size_t)offsets[key] + pos] = (uint32_t)i | (neg ? 0x80000000u : 0u);
-    });
+static int scan_excl(nzcb_ctx* ctx, const uint32_t* counts, uint32_t* offsets, size_t n) {
+    const size_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    uint32_t* sums = (uint32_t*)ctx->scratch_get("msm_scan_sums", (tiles + 1) * 4);
+    if (!sums) return ctx->fail(NZCB_E_NOMEM, "msm: cannot allocate scan workspace");
+    NZ_LAUNCH(ctx, k_scan_tile, (unsigned)tiles, SCAN_THREADS, 0, counts, offsets, sums, n);
+    NZ_LAUNCH(ctx, k_scan_tops, 1, 1024, 0, sums, tiles, offsets + n);
+    NZ_LAUNCH(ctx, k_scan_add, (unsigned)tiles, SCAN_THREADS, 0, offsets, sums, n);
+    return 0;
 }
 
-__global__ void __launch_bounds__(128) k_msm_accum(const G1Affine* __restrict__ bases, const uint32_t* __restrict__ sorted,
-                                                   const uint32_t* __restrict__ offsets, size_t nb,
-                                                   G1XYZZ* __restrict__ buckets) {
-    const size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= nb) return;
-    const uint32_t lo = offsets[b], hi = offsets[b + 1];
+// ---- step 4: accumulation over equal-length segments ----------------------------------------
+// Thread t owns sorted[t*L, (t+1)*L), L = max(LMIN, ceil(E / threads)) with E = offsets[n_keys] read on the
+// device (no host round trip).  Output per thread: two (key, partial) slots; every other bucket it meets lies
+// wholly inside its segment and is written straight to buckets[].
+constexpr uint32_t ACC_THREADS = 128, ACC_LMIN = 8;
+
+__global__ void __launch_bounds__(ACC_THREADS, 4)
+    k_msm_accum(const G1Affine* __restrict__ bases, const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ offsets,
+                uint32_t n_keys, G1XYZZ* __restrict__ buckets, uint32_t* __restrict__ pkeys, G1XYZZ* __restrict__ pvals) {
+    const uint32_t t = blockIdx.x * ACC_THREADS + threadIdx.x;
+    const uint32_t T = gridDim.x * ACC_THREADS;
+    const uint32_t E = offsets[n_keys];
+    uint32_t L = (E + T - 1) / T;
+    if (L < ACC_LMIN) L = ACC_LMIN;
+    const uint64_t lo64 = (uint64_t)t * L;
+    if (lo64 >= E) {
+        pkeys[2 * t] = KEY_NONE;
+        pkeys[2 * t + 1] = KEY_NONE;
+        return;
+    }
+    const uint32_t lo = (uint32_t)lo64;
+    const uint32_t hi = (uint64_t)lo + L < E ? lo + L : E;
+    // bucket of entry lo: the largest b with offsets[b] <= lo  (offsets[n_keys] = E > lo)
+    uint32_t b = 0, z = n_keys;
+    while (z - b > 1) {
+        const uint32_t m = (b + z) >> 1;
+        if (offsets[m] <= lo) b = m;
+        else z = m;
+    }
+    uint32_t next = offsets[b + 1];
     G1XYZZ acc = G1XYZZ::inf();
+    bool first = true;
+    uint32_t e = sorted[lo];
+    G1Affine p = bases[e & 0x7fffffffu];
     for (uint32_t k = lo; k < hi; k++) {
-        const uint32_t e = sorted[k];
-        G1Affine p = bases[e & 0x7fffffffu];
-        if (e & 0x80000000u) p.y = p.y.neg();  // (0,0) stays (0,0)
-        acc.add_affine(p);
+        // prefetch the next point while this one is added
+        const uint32_t e_cur = e;
+        const G1Affine p_cur = p;
+        if (k + 1 < hi) {
+            e = sorted[k + 1];
+            p = bases[e & 0x7fffffffu];
+        }
+        if (k == next) {  // bucket boundary: flush
+            if (first) {
+                pkeys[2 * t] = b;
+                pvals[2 * t] = acc;
+                first = false;
+            } else {
+                buckets[b] = acc;
+            }
+            acc = G1XYZZ::inf();
+            do {
+                b++;
+                next = offsets[b + 1];
+            } while (next == k);
+        }
+        G1Affine q = p_cur;
+        if (e_cur & 0x80000000u) q.y = q.y.neg();  // (0,0) stays (0,0)
+        acc.add_affine(q);
     }
-    buckets[b] = acc;
+    if (first) {
+        pkeys[2 * t] = b;
+        pvals[2 * t] = acc;
+        pkeys[2 * t + 1] = b;
+        pvals[2 * t + 1] = G1XYZZ::inf();
+    } else {
+        pkeys[2 * t + 1] = b;
+        pvals[2 * t + 1] = acc;
+    }
 }
 
-// per (window, chunk): run = sum B_k, acc = sum (k+1) * B_k over the chunk's S buckets
-__global__ void __launch_bounds__(128) k_msm_reduce1(const G1XYZZ* __restrict__ buckets, uint32_t W, uint32_t nbw,
-                                                     uint32_t C, uint32_t S, G1XYZZ* __restrict__ run_out,
-                                                     G1XYZZ* __restrict__ acc_out) {
-    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (size_t)W * C) return;
-    const uint32_t w = (uint32_t)(t / C), ch = (uint32_t)(t % C);
-    const G1XYZZ* B = buckets + (size_t)w * nbw + (size_t)ch * S;
+// One level of the segmented reduction of a key-sorted (key, partial) list: thread j sums runs of equal keys in
+// [j*L, (j+1)*L); runs strictly inside are complete -> buckets[key]; its first and last run go to the next list.
+// final != 0: single thread, everything is written to buckets.
+__global__ void __launch_bounds__(128) k_seg_level(const uint32_t* __restrict__ keys, const G1XYZZ* __restrict__ vals,
+                                                   uint32_t N, uint32_t L, G1XYZZ* __restrict__ buckets,
+                                                   uint32_t* __restrict__ okeys, G1XYZZ* __restrict__ ovals, int final) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t lo64 = (uint64_t)j * L;
+    if (lo64 >= N) return;
+    const uint32_t lo = (uint32_t)lo64;
+    const uint32_t hi = (uint64_t)lo + L < N ? lo + L : N;
+    uint32_t key = keys[lo];
+    G1XYZZ acc = key != KEY_NONE ? vals[lo] : G1XYZZ::inf();
+    bool first = !final;
+    for (uint32_t k = lo + 1; k < hi; k++) {
+        const uint32_t kk = keys[k];
+        if (kk != key) {
+            if (first) {
+                okeys[2 * j] = key;
+                ovals[2 * j] = acc;
+                first = false;
+            } else if (key != KEY_NONE) {
+                buckets[key] = acc;
+            }
+            key = kk;
+            acc = key != KEY_NONE ? vals[k] : G1XYZZ::inf();
+        } else if (key != KEY_NONE) {
+            acc.add(vals[k]);
+        }
+    }
+    if (final) {
+        if (key != KEY_NONE) buckets[key] = acc;
+    } else if (first) {
+        okeys[2 * j] = key;
+        ovals[2 * j] = acc;
+        okeys[2 * j + 1] = key;
+        ovals[2 * j + 1] = G1XYZZ::inf();
+    } else {
+        okeys[2 * j + 1] = key;
+        ovals[2 * j + 1] = acc;
+    }
+}
+
+// ---- step 5: R(X) = sum_b weight(b) X_b per bucket set, weight = b + 1 (one_based) or b -------
+// chunk ch of S = 2^log_S elements: run = sum X, acc = sum local_weight * X (+ the chunk's plain sums P);
+// R(X) = sum_ch acc_ch + R0(S * run)  ->  Xo[ch] = S * run_ch (zero-based next level), Po[ch] = acc_ch + sum P.
+__global__ void __launch_bounds__(128) k_bred(const G1XYZZ* __restrict__ X, const G1XYZZ* __restrict__ P, uint32_t total,
+                                              uint32_t log_S, int one_based, G1XYZZ* __restrict__ Xo,
+                                              G1XYZZ* __restrict__ Po) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const uint32_t S = 1u << log_S;
+    const G1XYZZ* x = X + (size_t)t * S;
     G1XYZZ run = G1XYZZ::inf(), acc = G1XYZZ::inf();
-    for (int k = (int)S - 1; k >= 0; k--) {
-        run.add(B[k]);
+    for (int k = (int)S - 1; k >= 1; k--) {
+        run.add(x[k]);
         acc.add(run);
     }
-    run_out[t] = run;
-    acc_out[t] = acc;
+    run.add(x[0]);
+    if (one_based) acc.add(run);
+    if (P) {
+        const G1XYZZ* pp = P + (size_t)t * S;
+        G1XYZZ pl = pp[0];
+        for (uint32_t k = 1; k < S; k++) pl.add(pp[k]);
+        acc.add(pl);
+    }
+    Po[t] = acc;
+    for (uint32_t i = 0; i < log_S; i++) run = run.dbl();
+    Xo[t] = run;
 }
 
-__device__ __forceinline__ G1XYZZ block_tree_sum(G1XYZZ* sh, G1XYZZ v, uint32_t C) {
-    const uint32_t t = threadIdx.x;
-    __syncthreads();
-    sh[t] = v;
-    __syncthreads();
-    for (uint32_t off = C >> 1; off >= 1; off >>= 1) {
-        if (t < off) {
-            G1XYZZ a = sh[t];
-            a.add(sh[t + off]);
-            sh[t] = a;
-        }
-        __syncthreads();
-    }
-    return sh[0];
-}
-
-// one block (C threads) per window: total_w = sum_ch acc_ch + S * sum_ch ch * run_ch
-__global__ void k_msm_reduce2(const G1XYZZ* __restrict__ run_in, const G1XYZZ* __restrict__ acc_in, uint32_t C,
-                              uint32_t log_C, uint32_t log_S, G1XYZZ* __restrict__ win_out) {
-    extern __shared__ __align__(32) unsigned char smem_raw[];
-    G1XYZZ* sh = reinterpret_cast<G1XYZZ*>(smem_raw);
-    const uint32_t w = blockIdx.x, t = threadIdx.x;
-    const G1XYZZ my_run = run_in[(size_t)w * C + t];
-    G1XYZZ total = block_tree_sum(sh, acc_in[(size_t)w * C + t], C);
-    G1XYZZ T = G1XYZZ::inf();
-    for (int j = (int)log_C - 1; j >= 0; j--) {
-        G1XYZZ pj = block_tree_sum(sh, ((t >> j) & 1) ? my_run : G1XYZZ::inf(), C);
-        if (t == 0) {
-            T = T.dbl();
-            T.add(pj);
-        }
-    }
-    if (t == 0) {
-        for (uint32_t i = 0; i < log_S; i++) T = T.dbl();
-        total.add(T);
-        win_out[w] = total;
-    }
-}
-
-__global__ void k_msm_final(const G1XYZZ* __restrict__ win, uint32_t W, uint32_t c, G1XYZZ* __restrict__ out) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// window mode: job k's result = sum_w 2^(c w) * set[k*W + w]   (Horner, one thread per job)
+__global__ void k_msm_horner(const G1XYZZ* __restrict__ sets, uint32_t W, uint32_t c, G1XYZZ* __restrict__ out) {
+    const uint32_t k = blockIdx.x;
+    if (threadIdx.x != 0) return;
     G1XYZZ r = G1XYZZ::inf();
     for (int w = (int)W - 1; w >= 0; w--) {
         for (uint32_t i = 0; i < c; i++) r = r.dbl();
-        r.add(win[w]);
+        r.add(sets[(size_t)k * W + w]);
     }
-    *out = r;
+    out[k] = r;
+}
+__global__ void k_copy_pts(const G1XYZZ* __restrict__ in, G1XYZZ* __restrict__ out, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i];
 }
 
-__global__ void k_set_inf(G1XYZZ* out) { *out = G1XYZZ::inf(); }
+__global__ void k_set_inf(G1XYZZ* out, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = G1XYZZ::inf();
+}
 
-int msm_dev(nzcb_ctx* ctx, const G1Affine* d_bases, const uint32_t* d_scalars, size_t n, bool mont, G1XYZZ* d_out) {
-    if (n == 0) {
-        NZ_LAUNCH(ctx, k_set_inf, 1, 1, 0, d_out);
+struct MsmJob {
+    const uint32_t* scalars;
+    size_t n;
+    bool mont;
+};
+
+static int msm_run(nzcb_ctx* ctx, const G1Affine* d_bases, const MsmPlan& p, const MsmJob* jobs, int K, G1XYZZ* d_out) {
+    size_t n_max = 0, n_sum = 0;
+    DigitArgs da;
+    memset(&da, 0, sizeof(da));
+    for (int k = 0; k < K; k++) {
+        if (jobs[k].n >= ((size_t)1 << 26)) return ctx->fail(NZCB_E_INVALID, "msm: n too large");
+        da.scalars[k] = jobs[k].scalars;
+        da.n[k] = (uint32_t)jobs[k].n;
+        da.mont[k] = jobs[k].mont ? 1 : 0;
+        n_max = std::max(n_max, jobs[k].n);
+        n_sum += jobs[k].n;
+    }
+    da.c = p.c; da.W = p.W; da.nbw = p.nbw; da.unified = p.unified ? 1 : 0; da.stride = p.stride;
+    const size_t n_keys = (size_t)p.G * p.nbw;
+    if (n_sum == 0) {
+        NZ_LAUNCH(ctx, k_set_inf, 1, 32, 0, d_out, (uint32_t)K);
         return 0;
     }
-    if (n >= ((size_t)1 << 31)) return ctx->fail(NZCB_E_INVALID, "msm: n too large");
-    const MsmPlan p = make_plan(n);
-    uint32_t* counts = (uint32_t*)ctx->scratch_get("msm_counts", (p.nb + 1) * 4);
-    uint32_t* offsets = (uint32_t*)ctx->scratch_get("msm_offsets", (p.nb + 1) * 4);
-    uint32_t* cursor = (uint32_t*)ctx->scratch_get("msm_cursor", (p.nb + 1) * 4);
-    uint32_t* sorted = (uint32_t*)ctx->scratch_get("msm_sorted", n * p.W * 4);
-    G1XYZZ* buckets = (G1XYZZ*)ctx->scratch_get("msm_buckets", p.nb * sizeof(G1XYZZ));
-    G1XYZZ* run = (G1XYZZ*)ctx->scratch_get("msm_run", (size_t)p.W * p.C * sizeof(G1XYZZ));
-    G1XYZZ* acc = (G1XYZZ*)ctx->scratch_get("msm_acc", (size_t)p.W * p.C * sizeof(G1XYZZ));
-    G1XYZZ* win = (G1XYZZ*)ctx->scratch_get("msm_win", (size_t)p.W * sizeof(G1XYZZ));
-    if (!counts || !offsets || !cursor || !sorted || !buckets || !run || !acc || !win)
-        return ctx->fail(NZCB_E_NOMEM, "msm: cannot allocate workspace for n=%zu", n);
-    NZ_CUDA(ctx, cudaMemsetAsync(counts, 0, (p.nb + 1) * 4, ctx->stream));
-    NZ_CUDA(ctx, cudaMemsetAsync(cursor, 0, (p.nb + 1) * 4, ctx->stream));
-    NZ_LAUNCH(ctx, k_msm_count, div_up(n, 256), 256, 0, d_scalars, n, mont ? 1 : 0, p.c, p.W, p.nbw, counts);
-    NZ_LAUNCH(ctx, k_scan_excl, 1, 1024, 0, counts, offsets, p.nb);
-    NZ_LAUNCH(ctx, k_msm_scatter, div_up(n, 256), 256, 0, d_scalars, n, mont ? 1 : 0, p.c, p.W, p.nbw, offsets, cursor,
-              sorted);
+    if (n_sum * p.W >= ((size_t)1 << 32) || n_keys >= ((size_t)1 << 31))
+        return ctx->fail(NZCB_E_INVALID, "msm: batch too large");
+
+    // accumulation grid: one resident wave
+    static int blocks_per_sm = 0;
+    if (!blocks_per_sm) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_msm_accum, ACC_THREADS, 0) != cudaSuccess ||
+            blocks_per_sm < 1)
+            blocks_per_sm = 1;
+    }
+    uint32_t acc_blocks = (uint32_t)ctx->sm_count * (uint32_t)blocks_per_sm;
+    {   // never more threads than ceil(max entries / LMIN)
+        const size_t need = (n_sum * p.W + (size_t)ACC_LMIN * ACC_THREADS - 1) / ((size_t)ACC_LMIN * ACC_THREADS);
+        if (need < acc_blocks) acc_blocks = (uint32_t)std::max<size_t>(1, need);
+    }
+    const uint32_t T1 = acc_blocks * ACC_THREADS;
+
+    uint32_t* counts = (uint32_t*)ctx->scratch_get("msm_counts", (n_keys + 1) * 4);
+    uint32_t* offsets = (uint32_t*)ctx->scratch_get("msm_offsets", (n_keys + 1) * 4);
+    uint32_t* sorted = (uint32_t*)ctx->scratch_get("msm_sorted", n_sum * p.W * 4);
+    G1XYZZ* buckets = (G1XYZZ*)ctx->scratch_get("msm_buckets", n_keys * sizeof(G1XYZZ));
+    uint32_t* pk0 = (uint32_t*)ctx->scratch_get("msm_pk0", (size_t)2 * T1 * 4);
+    uint32_t* pk1 = (uint32_t*)ctx->scratch_get("msm_pk1", (size_t)2 * T1 * 4);
+    G1XYZZ* pv0 = (G1XYZZ*)ctx->scratch_get("msm_pv0", (size_t)2 * T1 * sizeof(G1XYZZ));
+    G1XYZZ* pv1 = (G1XYZZ*)ctx->scratch_get("msm_pv1", (size_t)2 * T1 * sizeof(G1XYZZ));
+    // reduction ping-pong: level 1 output has n_keys / 2^log_S elements
+    const size_t red_cap = std::max<size_t>(n_keys / 2, p.G) + 1;
+    G1XYZZ* rx0 = (G1XYZZ*)ctx->scratch_get("msm_rx0", red_cap * sizeof(G1XYZZ));
+    G1XYZZ* rp0 = (G1XYZZ*)ctx->scratch_get("msm_rp0", red_cap * sizeof(G1XYZZ));
+    G1XYZZ* rx1 = (G1XYZZ*)ctx->scratch_get("msm_rx1", red_cap * sizeof(G1XYZZ));
+    G1XYZZ* rp1 = (G1XYZZ*)ctx->scratch_get("msm_rp1", red_cap * sizeof(G1XYZZ));
+    if (!counts || !offsets || !sorted || !buckets || !pk0 || !pk1 || !pv0 || !pv1 || !rx0 || !rp0 || !rx1 || !rp1)
+        return ctx->fail(NZCB_E_NOMEM, "msm: cannot allocate workspace for %zu scalars", n_sum);
+
+    // 1-3: sort the point references by bucket
+    NZ_CUDA(ctx, cudaMemsetAsync(counts, 0, (n_keys + 1) * 4, ctx->stream));
+    const dim3 dgrid(div_up(n_max, 256), (unsigned)K);
+    NZ_LAUNCH(ctx, k_msm_digits<true>, dgrid, 256, 0, da, counts, nullptr, nullptr);
+    NZ_TRY(scan_excl(ctx, counts, offsets, n_keys));
+    NZ_CUDA(ctx, cudaMemsetAsync(counts, 0, (n_keys + 1) * 4, ctx->stream));
+    NZ_LAUNCH(ctx, k_msm_digits<false>, dgrid, 256, 0, da, counts, offsets, sorted);
+    NZ_CUDA(ctx, cudaMemsetAsync(buckets, 0, n_keys * sizeof(G1XYZZ), ctx->stream));  // ZZ = 0: infinity
+
+    // 4: accumulate
     if (ctx->prof_on) {
         if (ctx->prof_used == ctx->prof_ev.size()) {
             cudaEvent_t a, b;
@@ -245,23 +471,114 @@ int msm_dev(nzcb_ctx* ctx, const G1Affine* d_bases, const uint32_t* d_scalars, s
         }
         NZ_CUDA(ctx, cudaEventRecord(ctx->prof_ev[ctx->prof_used].first, ctx->stream));
     }
-    NZ_LAUNCH(ctx, k_msm_accum, div_up(p.nb, 128), 128, 0, d_bases, sorted, offsets, p.nb, buckets);
+    NZ_LAUNCH(ctx, k_msm_accum, acc_blocks, ACC_THREADS, 0, d_bases, sorted, offsets, (uint32_t)n_keys, buckets, pk0, pv0);
     if (ctx->prof_on) {
         NZ_CUDA(ctx, cudaEventRecord(ctx->prof_ev[ctx->prof_used].second, ctx->stream));
         ctx->prof_used++;
-        ctx->prof_modmul += 160.0 * (double)n;
+        ctx->prof_modmul += 160.0 * (double)n_sum;
     }
-    NZ_LAUNCH(ctx, k_msm_reduce1, div_up((size_t)p.W * p.C, 128), 128, 0, buckets, p.W, p.nbw, p.C, p.S, run, acc);
-    NZ_LAUNCH(ctx, k_msm_reduce2, p.W, p.C, p.C * sizeof(G1XYZZ), run, acc, p.C, p.log_C, p.log_S, win);
-    NZ_LAUNCH(ctx, k_msm_final, 1, 32, 0, win, p.W, p.c, d_out);
+    {
+        uint32_t N = 2 * T1;
+        uint32_t *ki = pk0, *ko = pk1;
+        G1XYZZ *vi = pv0, *vo = pv1;
+        uint32_t L = 8;
+        while (N > 32) {
+            const uint32_t threads = (N + L - 1) / L;
+            NZ_LAUNCH(ctx, k_seg_level, div_up(threads, 128), 128, 0, ki, vi, N, L, buckets, ko, vo, 0);
+            N = 2 * threads;
+            std::swap(ki, ko);
+            std::swap(vi, vo);
+            L = 32;
+        }
+        NZ_LAUNCH(ctx, k_seg_level, 1, 32, 0, ki, vi, N, N, buckets, ko, vo, 1);
+    }
+
+    // 5: bucket reduction, all sets at once
+    const G1XYZZ* X = buckets;
+    const G1XYZZ* P = nullptr;
+    G1XYZZ *xo = rx0, *po = rp0, *xo2 = rx1, *po2 = rp1;
+    uint32_t bits = p.c - 1;  // log2 of the per-set length
+    int one_based = 1;
+    while (bits > 0) {
+        const uint32_t log_S = bits >= 3 ? 3 : bits;
+        bits -= log_S;
+        const uint32_t total = p.G << bits;
+        NZ_LAUNCH(ctx, k_bred, div_up(total, 128), 128, 0, X, P, total, log_S, one_based, xo, po);
+        X = xo;
+        P = po;
+        std::swap(xo, xo2);
+        std::swap(po, po2);
+        one_based = 0;
+    }
+    // now P[g] = set g's weighted sum (c == 1 cannot happen: c >= 2)
+    if (p.unified) {
+        NZ_LAUNCH(ctx, k_copy_pts, 1, 32, 0, P, d_out, (uint32_t)K);
+    } else {
+        NZ_LAUNCH(ctx, k_msm_horner, (unsigned)K, 32, 0, P, p.W, p.c, d_out);
+    }
     return 0;
 }
 
-int msm_to_host_affine(nzcb_ctx* ctx, const G1XYZZ* d_pt, G1Affine* h_out) {
-    G1XYZZ h;
-    NZ_CUDA(ctx, cudaMemcpyAsync(&h, d_pt, sizeof(G1XYZZ), cudaMemcpyDeviceToHost, ctx->stream));
+// ---- fixed-base tables -----------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_table_build(const G1Affine* __restrict__ bases, uint32_t n, uint32_t stride,
+                                                     uint32_t c, uint32_t W, G1Affine* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const G1Affine P = bases[i];
+    out[i] = P;
+    G1XYZZ acc = G1XYZZ::from_affine(P);
+    for (uint32_t w = 1; w < W; w++) {
+        for (uint32_t j = 0; j < c; j++) acc = acc.dbl();
+        out[(size_t)w * stride + i] = acc.to_affine();
+    }
+}
+
+int g1_table_build(nzcb_ctx* ctx, const G1Affine* d_bases, size_t n, G1Table* out) {
+    if (n == 0 || n >= ((size_t)1 << 26)) return ctx->fail(NZCB_E_INVALID, "g1 table: bad size %zu", n);
+    out->n = n;
+    out->stride = n;
+    out->c = msm_table_window(n);
+    out->W = 254 / out->c + 1;
+    if ((size_t)out->W * n >= ((size_t)1 << 31)) return ctx->fail(NZCB_E_INVALID, "g1 table: too many points");
+    if (cudaMalloc(&out->pts, (size_t)out->W * n * sizeof(G1Affine)) != cudaSuccess) {
+        cudaGetLastError();
+        out->pts = nullptr;
+        return ctx->fail(NZCB_E_NOMEM, "g1 table: cannot allocate %zu bytes", (size_t)out->W * n * sizeof(G1Affine));
+    }
+    NZ_LAUNCH(ctx, k_table_build, div_up(n, 128), 128, 0, d_bases, (uint32_t)n, (uint32_t)n, out->c, out->W, out->pts);
+    return 0;
+}
+
+void g1_table_free(G1Table* t) {
+    if (t && t->pts) cudaFree(t->pts);
+    if (t) t->pts = nullptr;
+}
+
+int msm_table_dev(nzcb_ctx* ctx, const G1Table& tab, const uint32_t* const* d_scalars, const size_t* n, int K,
+                  bool scalars_mont, G1XYZZ* d_out) {
+    if (K < 1 || K > NZ_MSM_MAXJOBS) return ctx->fail(NZCB_E_INVALID, "msm: 1..%d jobs per batch", NZ_MSM_MAXJOBS);
+    MsmJob jobs[NZ_MSM_MAXJOBS];
+    for (int k = 0; k < K; k++) {
+        if (n[k] > tab.n) return ctx->fail(NZCB_E_INVALID, "msm: %zu scalars for a table of %zu bases", n[k], tab.n);
+        jobs[k] = MsmJob{d_scalars[k], n[k], scalars_mont};
+    }
+    MsmPlan p;
+    p.c = tab.c; p.W = tab.W; p.nbw = 1u << (tab.c - 1); p.G = (uint32_t)K; p.unified = true; p.stride = (uint32_t)tab.stride;
+    return msm_run(ctx, tab.pts, p, jobs, K, d_out);
+}
+
+int msm_dev(nzcb_ctx* ctx, const G1Affine* d_bases, const uint32_t* d_scalars, size_t n, bool mont, G1XYZZ* d_out) {
+    const MsmJob job{d_scalars, n, mont};
+    const MsmPlan p = make_plan_window(n, 1);
+    return msm_run(ctx, d_bases, p, &job, 1, d_out);
+}
+
+int msm_to_host_affine(nzcb_ctx* ctx, const G1XYZZ* d_pt, G1Affine* h_out, int count) {
+    G1XYZZ h[NZ_MSM_MAXJOBS];
+    if (count < 1 || count > NZ_MSM_MAXJOBS) return ctx->fail(NZCB_E_INVALID, "msm: bad point count");
+    NZ_CUDA(ctx, cudaMemcpyAsync(h, d_pt, (size_t)count * sizeof(G1XYZZ), cudaMemcpyDeviceToHost, ctx->stream));
     NZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    *h_out = h.to_affine();  // one Fq inversion on the host: O(1) finishing step
+    for (int i = 0; i < count; i++) h_out[i] = h[i].to_affine();  // one Fq inversion each on the host: O(1) finishing step
     return 0;
 }
 
@@ -269,16 +586,76 @@ int msm_to_host_affine(nzcb_ctx* ctx, const G1XYZZ* d_pt, G1Affine* h_out) {
 
 using namespace nzcb;
 
+struct nzcb_g1_table {
+    nzcb_ctx* ctx;
+    G1Table tab;
+};
+
+extern "C" int32_t nzcb_g1_table_create(nzcb_ctx* ctx, const uint8_t* bases, size_t n, nzcb_g1_table** out) {
+    if (!ctx || !bases || !out || n == 0) return NZCB_E_INVALID;
+    *out = nullptr;
+    NZ_CUDA(ctx, cudaSetDevice(ctx->device));
+    G1Affine* d_b = (G1Affine*)ctx->scratch_get("msm_in_bases", n * 64 + 64);
+    if (!d_b) return ctx->fail(NZCB_E_NOMEM, "g1 table: cannot allocate input buffer for n=%zu", n);
+    NZ_CUDA(ctx, cudaMemcpyAsync(d_b, bases, n * 64, cudaMemcpyHostToDevice, ctx->stream));
+    nzcb_g1_table* t = new nzcb_g1_table();
+    t->ctx = ctx;
+    const int rc = g1_table_build(ctx, d_b, n, &t->tab);
+    if (rc != 0 || cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+        g1_table_free(&t->tab);
+        delete t;
+        return rc ? rc : ctx->fail(NZCB_E_CUDA, "g1 table: build failed");
+    }
+    *out = t;
+    return 0;
+}
+
+extern "C" void nzcb_g1_table_free(nzcb_g1_table* t) {
+    if (!t) return;
+    if (t->ctx) {
+        cudaSetDevice(t->ctx->device);
+        cudaStreamSynchronize(t->ctx->stream);
+    }
+    g1_table_free(&t->tab);
+    delete t;
+}
+
+// K MSMs over the first n[k] bases of the table, scalars device resident (n x 32 B LE canonical each)
+extern "C" int32_t nzcb_msm_g1_table_dev(nzcb_ctx* ctx, const nzcb_g1_table* t, const void* const* d_scalars,
+                                         const size_t* n, int32_t K, uint8_t* out /* K x 64 */) {
+    if (!ctx || !t || !d_scalars || !n || !out || t->ctx != ctx) return NZCB_E_INVALID;
+    G1XYZZ* d_out = (G1XYZZ*)ctx->scratch_get("msm_out", NZ_MSM_MAXJOBS * sizeof(G1XYZZ));
+    if (!d_out) return ctx->fail(NZCB_E_NOMEM, "msm: out of device memory");
+    NZ_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    NZ_TRY(msm_table_dev(ctx, t->tab, (const uint32_t* const*)d_scalars, n, K, false, d_out));
+    NZ_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    G1Affine a[NZ_MSM_MAXJOBS];
+    NZ_TRY(msm_to_host_affine(ctx, d_out, a, K));
+    cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1);
+    memcpy(out, a, (size_t)K * 64);
+    return 0;
+}
+
+extern "C" int32_t nzcb_msm_g1_table(nzcb_ctx* ctx, const nzcb_g1_table* t, const uint8_t* scalars, size_t n,
+                                     uint8_t out[64]) {
+    if (!ctx || !t || !out || (n && !scalars) || t->ctx != ctx) return NZCB_E_INVALID;
+    uint32_t* d_s = (uint32_t*)ctx->scratch_get("msm_in_scalars", n * 32 + 32);
+    if (!d_s) return ctx->fail(NZCB_E_NOMEM, "msm: cannot allocate input buffers for n=%zu", n);
+    if (n) NZ_CUDA(ctx, cudaMemcpyAsync(d_s, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    const void* sp = d_s;
+    return nzcb_msm_g1_table_dev(ctx, t, &sp, &n, 1, out);
+}
+
 extern "C" int32_t nzcb_msm_g1_dev(nzcb_ctx* ctx, const void* d_bases, const void* d_scalars, size_t n,
                                    uint8_t out[64]) {
     if (!ctx || !out || (n && (!d_bases || !d_scalars))) return NZCB_E_INVALID;
-    G1XYZZ* d_out = (G1XYZZ*)ctx->scratch_get("msm_out", sizeof(G1XYZZ));
+    G1XYZZ* d_out = (G1XYZZ*)ctx->scratch_get("msm_out", NZ_MSM_MAXJOBS * sizeof(G1XYZZ));
     if (!d_out) return ctx->fail(NZCB_E_NOMEM, "msm: out of device memory");
     NZ_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     NZ_TRY(msm_dev(ctx, (const G1Affine*)d_bases, (const uint32_t*)d_scalars, n, false, d_out));
     NZ_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     G1Affine a;
-    NZ_TRY(msm_to_host_affine(ctx, d_out, &a));
+    NZ_TRY(msm_to_host_affine(ctx, d_out, &a, 1));
     cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1);
     memcpy(out, &a, 64);
     return 0;

@@ -27,7 +27,7 @@ struct nzcb_zkey {
     Fr* d_q[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // n coefs then 4n evals each
     Fr* d_sigma = nullptr;                                       // 3 x (n + 4n)
     Fr* d_lag = nullptr;                                         // max(nPublic,1) x (n + 4n)
-    G1Affine* d_ptau = nullptr;                                  // n + 6
+    G1Table tab;                                                 // [tau^i]G1, i < n + 6, with window shifts (msm.cu)
 };
 
 namespace {
@@ -336,7 +336,7 @@ extern "C" void nzcb_zkey_free(nzcb_zkey* zk) {
     for (int i = 0; i < 5; i++) cudaFree(zk->d_q[i]);
     cudaFree(zk->d_sigma);
     cudaFree(zk->d_lag);
-    cudaFree(zk->d_ptau);
+    g1_table_free(&zk->tab);
     delete zk;
 }
 
@@ -420,8 +420,19 @@ extern "C" int32_t nzcb_zkey_load(nzcb_ctx* ctx, const uint8_t* data, size_t len
     ZK_CUDA(cudaMemcpyAsync(zk->d_sigma, sec[12].p, sec[12].size, cudaMemcpyHostToDevice, ctx->stream));
     ZK_CUDA(cudaMalloc(&zk->d_lag, sec[13].size));
     ZK_CUDA(cudaMemcpyAsync(zk->d_lag, sec[13].p, sec[13].size, cudaMemcpyHostToDevice, ctx->stream));
-    ZK_CUDA(cudaMalloc(&zk->d_ptau, sec[14].size));
-    ZK_CUDA(cudaMemcpyAsync(zk->d_ptau, sec[14].p, sec[14].size, cudaMemcpyHostToDevice, ctx->stream));
+    {   // SRS: upload section 14 and precompute the window shifts 2^(c w) [tau^i]G1 once per key
+        G1Affine* d_ptau = (G1Affine*)ctx->scratch_get("zk_ptau_in", sec[14].size);
+        if (!d_ptau) {
+            nzcb_zkey_free(zk);
+            return ctx->fail(NZCB_E_NOMEM, "zkey: cannot allocate the SRS staging buffer");
+        }
+        ZK_CUDA(cudaMemcpyAsync(d_ptau, sec[14].p, sec[14].size, cudaMemcpyHostToDevice, ctx->stream));
+        const int rc = g1_table_build(ctx, d_ptau, n + 6, &zk->tab);
+        if (rc != 0) {
+            nzcb_zkey_free(zk);
+            return rc;
+        }
+    }
 
     // additions: level-schedule.  level(i) = 1 + max(level of operands that are themselves additions)
     const uint32_t n_w = zk->n_vars - zk->n_add;
@@ -484,7 +495,7 @@ namespace {
 
 struct Bufs {
     Fr *W, *A, *B, *C, *pol_a, *pol_b, *pol_c, *pol_z, *A4, *B4, *C4, *Z4, *num, *den, *T, *Tz, *pol_r, *pol_wxi,
-        *quot, *vals, *pub;
+        *quot, *quot2, *vals, *pub;
     G1XYZZ* pts;
     int* flags;
 };
@@ -516,6 +527,7 @@ int get_bufs(nzcb_ctx* ctx, const nzcb_zkey* zk, Bufs& b) {
     GETBUF(pol_r, "pv_pol_r", n + 8);
     GETBUF(pol_wxi, "pv_pol_wxi", n + 8);
     GETBUF(quot, "pv_quot", n + 8);
+    GETBUF(quot2, "pv_quot2", n + 8);
     GETBUF(vals, "pv_vals", 16);
     GETBUF(pub, "pv_pub", zk->n_public + 1);
     GETBUF(pts, "pv_pts", 4);
@@ -650,12 +662,14 @@ int prove_core(nzcb_ctx* ctx, const nzcb_zkey* zk, const Fr* d_w_le, const uint8
     }
     tr_.mark("r1 ntt");
     G1Affine cA, cB, cC, cZ, cT1, cT2, cT3, cWxi, cWxiw;
-    NZ_TRY(msm_dev(ctx, zk->d_ptau, (const uint32_t*)b.pol_a, (size_t)n + 2, true, b.pts + 0));
-    NZ_TRY(msm_to_host_affine(ctx, b.pts + 0, &cA));
-    NZ_TRY(msm_dev(ctx, zk->d_ptau, (const uint32_t*)b.pol_b, (size_t)n + 2, true, b.pts + 1));
-    NZ_TRY(msm_to_host_affine(ctx, b.pts + 1, &cB));
-    NZ_TRY(msm_dev(ctx, zk->d_ptau, (const uint32_t*)b.pol_c, (size_t)n + 2, true, b.pts + 2));
-    NZ_TRY(msm_to_host_affine(ctx, b.pts + 2, &cC));
+    {
+        const uint32_t* sc[3] = {(const uint32_t*)b.pol_a, (const uint32_t*)b.pol_b, (const uint32_t*)b.pol_c};
+        const size_t sn[3] = {(size_t)n + 2, (size_t)n + 2, (size_t)n + 2};
+        G1Affine r[3];
+        NZ_TRY(msm_table_dev(ctx, zk->tab, sc, sn, 3, true, b.pts));
+        NZ_TRY(msm_to_host_affine(ctx, b.pts, r, 3));
+        cA = r[0]; cB = r[1]; cC = r[2];
+    }
     g1_to_be(cA, out->A);
     g1_to_be(cB, out->B);
     g1_to_be(cC, out->C);
@@ -715,8 +729,12 @@ int prove_core(nzcb_ctx* ctx, const nzcb_zkey* zk, const Fr* d_w_le, const uint8
         NZ_TRY(to4t(ctx, zk, b.den, b.pol_z, b.Z4, pz, 3));
     }
     tr_.mark("r2 ntt");
-    NZ_TRY(msm_dev(ctx, zk->d_ptau, (const uint32_t*)b.pol_z, (size_t)n + 3, true, b.pts + 0));
-    NZ_TRY(msm_to_host_affine(ctx, b.pts + 0, &cZ));
+    {
+        const uint32_t* sc[1] = {(const uint32_t*)b.pol_z};
+        const size_t sn[1] = {(size_t)n + 3};
+        NZ_TRY(msm_table_dev(ctx, zk->tab, sc, sn, 1, true, b.pts));
+        NZ_TRY(msm_to_host_affine(ctx, b.pts, &cZ, 1));
+    }
     g1_to_be(cZ, out->Z);
 
     tr_.mark("r2 msm");
@@ -754,12 +772,14 @@ int prove_core(nzcb_ctx* ctx, const nzcb_zkey* zk, const Fr* d_w_le, const uint8
     }
     tr_.mark("r3 intt x2");
     Fr* pol_t = b.T;  // 3n + 6 coefficients
-    NZ_TRY(msm_dev(ctx, zk->d_ptau, (const uint32_t*)pol_t, N, true, b.pts + 0));
-    NZ_TRY(msm_to_host_affine(ctx, b.pts + 0, &cT1));
-    NZ_TRY(msm_dev(ctx, zk->d_ptau, (const uint32_t*)(pol_t + N), N, true, b.pts + 1));
-    NZ_TRY(msm_to_host_affine(ctx, b.pts + 1, &cT2));
-    NZ_TRY(msm_dev(ctx, zk->d_ptau, (const uint32_t*)(pol_t + 2 * N), N + 6, true, b.pts + 2));
-    NZ_TRY(msm_to_host_affine(ctx, b.pts + 2, &cT3));
+    {
+        const uint32_t* sc[3] = {(const uint32_t*)pol_t, (const uint32_t*)(pol_t + N), (const uint32_t*)(pol_t + 2 * N)};
+        const size_t sn[3] = {N, N, N + 6};
+        G1Affine r[3];
+        NZ_TRY(msm_table_dev(ctx, zk->tab, sc, sn, 3, true, b.pts));
+        NZ_TRY(msm_to_host_affine(ctx, b.pts, r, 3));
+        cT1 = r[0]; cT2 = r[1]; cT3 = r[2];
+    }
     g1_to_be(cT1, out->T1);
     g1_to_be(cT2, out->T2);
     g1_to_be(cT3, out->T3);
@@ -837,14 +857,18 @@ int prove_core(nzcb_ctx* ctx, const nzcb_zkey* zk, const Fr* d_w_le, const uint8
     }
     NZ_TRY(poly_horner(ctx, b.pol_wxi, N + 6, xi, b.vals + 9, b.quot));
     tr_.mark("r5 wxi poly");
-    NZ_TRY(msm_dev(ctx, zk->d_ptau, (const uint32_t*)b.quot, N + 6, true, b.pts + 0));
-    NZ_TRY(msm_to_host_affine(ctx, b.pts + 0, &cWxi));
     // W_{xi w} = (pol_z - eval_zw) / (X - xi w)
     NZ_CUDA(ctx, cudaMemcpyAsync(b.pol_wxi, b.pol_z, (N + 3) * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->stream));
     NZ_LAUNCH(ctx, k_sub_at0, 1, 1, 0, b.pol_wxi, ezw);
-    NZ_TRY(poly_horner(ctx, b.pol_wxi, N + 3, xiw, b.vals + 10, b.quot));
-    NZ_TRY(msm_dev(ctx, zk->d_ptau, (const uint32_t*)b.quot, N + 3, true, b.pts + 1));
-    NZ_TRY(msm_to_host_affine(ctx, b.pts + 1, &cWxiw));
+    NZ_TRY(poly_horner(ctx, b.pol_wxi, N + 3, xiw, b.vals + 10, b.quot2));
+    {
+        const uint32_t* sc[2] = {(const uint32_t*)b.quot, (const uint32_t*)b.quot2};
+        const size_t sn[2] = {N + 6, N + 3};
+        G1Affine r[2];
+        NZ_TRY(msm_table_dev(ctx, zk->tab, sc, sn, 2, true, b.pts));
+        NZ_TRY(msm_to_host_affine(ctx, b.pts, r, 2));
+        cWxi = r[0]; cWxiw = r[1];
+    }
     tr_.mark("r5 rest");
     Fr rem[2];
     NZ_CUDA(ctx, cudaMemcpyAsync(rem, b.vals + 9, 2 * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));

@@ -48,3 +48,54 @@ class _G1:
 
 Fr = _Fr()
 G1 = _G1()
+
+
+class G1Table:
+    """Fixed bases with precomputed window shifts (nzcb_g1_table_*): how the prover holds the zkey's SRS.
+    multiExpAffine over the first n bases; `batch` runs up to four MSMs as one sort + accumulation."""
+
+    def __init__(self, buffBases, ctx=None):
+        self.ctx = ctx or default_context()
+        self.n = len(buffBases) // 64
+        h = ctypes.c_void_p()
+        b = (ctypes.c_uint8 * len(buffBases)).from_buffer_copy(buffBases)
+        self.ctx.check(self.ctx.lib.nzcb_g1_table_create(self.ctx.h, b, self.n, ctypes.byref(h)))
+        self.h = h
+
+    def multiExpAffine(self, buffScalars):
+        n = len(buffScalars) // 32
+        out = (ctypes.c_uint8 * 64)()
+        s = (ctypes.c_uint8 * max(1, len(buffScalars))).from_buffer_copy(buffScalars or b"\0")
+        self.ctx.check(self.ctx.lib.nzcb_msm_g1_table(self.ctx.h, self.h, s, n, out))
+        return bytes(out)
+
+    def batch(self, scalar_buffers):
+        """[scalars bytes, ...] (<= 4) -> [affine LEM bytes, ...]"""
+        K = len(scalar_buffers)
+        ctx = self.ctx
+        dptrs = []
+        for sb in scalar_buffers:
+            d = ctx.dev_alloc(max(32, len(sb)))
+            if sb:
+                ctx.dev_upload(d, sb)
+            dptrs.append(d)
+        arr = (ctypes.c_void_p * K)(*[d.value if isinstance(d, ctypes.c_void_p) else d for d in dptrs])
+        ns = (ctypes.c_size_t * K)(*[len(sb) // 32 for sb in scalar_buffers])
+        out = (ctypes.c_uint8 * (64 * K))()
+        try:
+            ctx.check(ctx.lib.nzcb_msm_g1_table_dev(ctx.h, self.h, arr, ns, K, out))
+        finally:
+            for d in dptrs:
+                ctx.dev_free(d)
+        return [bytes(out[64 * k:64 * (k + 1)]) for k in range(K)]
+
+    def close(self):
+        if getattr(self, "h", None) and self.ctx.h:
+            self.ctx.lib.nzcb_g1_table_free(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -30,8 +30,9 @@ class CircuitProver:
         self.vk = None
         self.verbose = verbose
 
-    def setup(self, srs_g1_lem=None):
-        """powersoftau + plonk setup on the GPU, zkey made device resident; returns the vk object"""
+    def setup(self, srs_g1_lem=None, keep_zkey=False):
+        """powersoftau + plonk setup on the GPU, zkey made device resident; returns the vk object
+        (or the zkey file bytes with keep_zkey=True, for callers that also want to write it out)"""
         from .snarkjs import R_MOD as _R
         art = self.art
         t = time.time()
@@ -53,6 +54,8 @@ class CircuitProver:
         self.zk = ZKey(zkey, self.ctx)
         self.timings["zkey_load"] = time.time() - t
         self.zkey_bytes_len = len(zkey)
+        if keep_zkey:
+            return zkey
         del zkey
         return self.vk
 

@@ -105,3 +105,81 @@ def test_msm_small_scalars(ctx):
     scal = b"".join(b.to_le(s) for s in sc)
     got = b.g1_from_lem(G1.multiExpAffine(bases, scal, ctx))
     assert got == b.g1_msm(pts, sc)
+
+
+# ---- fixed-base table mode (how the prover runs its nine MSMs) ------------------------------
+@pytest.mark.parametrize("n", [1, 2, 33, 100, 1000, 5000])
+def test_table_msm_matches_oracle(ctx, n):
+    from nzcb_circom_b200.ffjavascript import G1Table
+
+    rng = random.Random(n + 7)
+    pts = _points(rng, n)
+    if n >= 33:
+        pts[5] = None
+        pts[7] = pts[6]
+        pts[9] = b.g1_neg(pts[8])
+    tab = G1Table(b"".join(b.g1_to_lem(P) for P in pts), ctx)
+    sc = [rng.randrange(b.R_MOD) for _ in range(n)]
+    if n >= 33:
+        sc[0], sc[1], sc[2], sc[3] = 0, b.R_MOD - 1, 1, (b.R_MOD - 1) // 2
+        sc[4] = (b.R_MOD + 1) // 2
+        sc[7] = sc[6]
+        sc[9] = sc[8]
+    assert b.g1_from_lem(tab.multiExpAffine(b"".join(b.to_le(s) for s in sc))) == b.g1_msm(pts, sc)
+    # a prefix of the bases, and a batch of jobs of different lengths (A/B/C, T1/T2/T3 style)
+    m = max(1, n // 2)
+    jobs = [sc, [rng.randrange(b.R_MOD) for _ in range(m)], [rng.choice([0, 1, b.R_MOD - 1, 255]) for _ in range(n)]]
+    got = tab.batch([b"".join(b.to_le(s) for s in j) for j in jobs])
+    for j, g in zip(jobs, got):
+        assert b.g1_from_lem(g) == b.g1_msm(pts[:len(j)], j)
+    tab.close()
+
+
+def test_table_msm_giant_buckets(ctx):
+    """all scalars equal: one bucket per window holds every point (the segmented reduction's worst case)"""
+    from nzcb_circom_b200.ffjavascript import G1Table
+
+    rng = random.Random(5)
+    n = 3000
+    pts = _points(rng, n)
+    tab = G1Table(b"".join(b.g1_to_lem(P) for P in pts), ctx)
+    S = None
+    for P in pts:
+        S = b.g1_add(S, P)
+    for s in (1, b.R_MOD - 1, 0x1234567, rng.randrange(b.R_MOD)):
+        got = b.g1_from_lem(tab.multiExpAffine(b.to_le(s) * n))
+        assert got == b.g1_mul(S, s)
+    tab.close()
+
+
+@pytest.mark.parametrize("log_n", [16, 21])
+def test_table_msm_srs_identity_large(ctx, log_n):
+    """sum_i c_i [tau^i]G == p(tau) G for the synthetic SRS, full-size scalars and wire-like small ones;
+    table mode and one-shot window mode agree bit for bit."""
+    import numpy as np
+    from nzcb_circom_b200.ffjavascript import G1, G1Table
+    from nzcb_circom_b200.snarkjs import powersoftau
+    from oracle.keccak import hash_to_fr
+
+    tau = hash_to_fr(b"nzcb-b200-tau")
+    n = (1 << log_n) + 6
+    srs = powersoftau.new_g1(tau, n, ctx)
+    tab = G1Table(srs, ctx)
+    rng = np.random.default_rng(log_n)
+    raw = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    raw[:, 31] &= 0x1F  # < 2^253 < r
+    small = np.zeros((n, 32), dtype=np.uint8)
+    small[:, 0] = rng.integers(0, 2, size=n, dtype=np.uint8)
+    small[::7, 0] = rng.integers(0, 256, size=len(small[::7]), dtype=np.uint8)
+    for arr in (raw, small):
+        buf = arr.tobytes()
+        # p(tau) by Horner over numpy-decoded ints would be slow in Python at 2^21: use chunks of 8 bytes
+        coef = [int.from_bytes(buf[i * 32:(i + 1) * 32], "little") for i in range(n)]
+        acc = 0
+        for c in reversed(coef):
+            acc = (acc * tau + c) % b.R_MOD
+        exp = b.g1_mul(b.G1_GEN, acc)
+        got_t = tab.multiExpAffine(buf)
+        assert b.g1_from_lem(got_t) == exp
+        assert G1.multiExpAffine(srs, buf, ctx) == got_t
+    tab.close()
