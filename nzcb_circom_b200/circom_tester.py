@@ -129,17 +129,18 @@ def compile_circuit(name, use_cache=True):
     """circom stand-in: build the named main component -> Artifact (.r1cs + witness program).
     Big circuits are cached on disk under _cache/ like circom's own build outputs."""
     import pickle
+    import zlib
     key = os.path.splitext(os.path.basename(name))[0]
     key = _ALIAS.get(key, key)
     if key not in MAINS:
         raise FileNotFoundError(f"no main component known for {name}")
     if key in _compiled:
         return _compiled[key]
-    path = os.path.join(_CACHE_DIR, f"{key}-{_source_tag()}.pkl")
+    path = os.path.join(_CACHE_DIR, f"{key}-{_source_tag()}.pkz")
     if use_cache and os.path.exists(path):
         try:
             with open(path, "rb") as fh:
-                _compiled[key] = pickle.load(fh)
+                _compiled[key] = pickle.loads(zlib.decompress(fh.read()))
             return _compiled[key]
         except Exception:
             pass
@@ -151,7 +152,7 @@ def compile_circuit(name, use_cache=True):
         os.makedirs(_CACHE_DIR, exist_ok=True)
         tmp = path + f".tmp{os.getpid()}"
         with open(tmp, "wb") as fh:
-            pickle.dump(art, fh, protocol=4)
+            fh.write(zlib.compress(pickle.dumps(art, protocol=4), 1))
         os.replace(tmp, path)
     return _compiled[key]
 

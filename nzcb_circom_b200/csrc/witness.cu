@@ -15,18 +15,22 @@
 // the |x| <= 1024 operands the CBOR selectors produce and
 // falls back to a Fermat inverse otherwise.
 #include "common.cuh"
+#include <algorithm>
 
 using namespace nzcb;
 
 enum { OP_LIN = 1, OP_MUL = 2, OP_BITS = 3, OP_INV = 4, OP_ASSERT = 5 };
 constexpr uint32_t NZ_INV_TAB = 1024;
+constexpr uint32_t NZ_LONG_LC = 24;  // an LC (or bit decomposition) longer than this is evaluated by a whole warp
 
 struct nzcb_circuit {
     nzcb_ctx* ctx = nullptr;
     uint32_t n_total = 0, n_witness = 0, n_out = 0, n_in = 0, n_consts = 0, n_instr = 0, n_levels = 0, n_code = 0;
     Fr* d_consts = nullptr;      // Montgomery
-    uint32_t* d_ioff = nullptr;
+    Fr* d_consts_can = nullptr;  // canonical
+    uint32_t* d_ioff = nullptr;  // instruction offsets; inside a level the long instructions come first
     uint32_t* d_lstart = nullptr;
+    uint32_t* d_nlong = nullptr; // per level: how many leading instructions run one-per-warp
     uint32_t* d_code = nullptr;
     Fr* d_invtab = nullptr;      // canonical 1/k, k = 0..NZ_INV_TAB (entry 0 unused)
 };
@@ -34,44 +38,143 @@ struct nzcb_circuit {
 namespace {
 
 struct ProgView {
-    const Fr* consts;
-    const uint32_t *ioff, *lstart, *code;
+    const Fr* consts;      // Montgomery
+    const Fr* consts_can;  // canonical
+    const uint32_t *ioff, *lstart, *nlong, *code;
     const Fr* invtab;
     uint32_t n_total, n_out, n_in, n_levels;
 };
 
-// canonical value of  k + sum coef_i * w_i ;  advances p past the encoded LC
+__device__ __forceinline__ bool fits_u32(const Fr& v) {
+    uint32_t hi = 0;
+#pragma unroll
+    for (int i = 1; i < 8; i++) hi |= v.v[i];
+    return hi == 0;
+}
+
+// acc += coef_c * v  for one LC term (canonical values; coefficient index c: 0 = +1, 1 = -1)
+__device__ __forceinline__ void lc_term(const ProgView& pv, Fr& acc, uint32_t c, const Fr& v) {
+    if (c == 0) acc = acc + v;
+    else if (c == 1) acc = acc - v;
+    else if (v.is_zero()) return;
+    else if (fits_u32(v) && v.v[0] == 1) acc = acc + pv.consts_can[c];  // bit wires: no multiply
+    else acc = acc + pv.consts[c] * v;  // Montgomery const x canonical wire = canonical
+}
+
+// canonical value of  k + sum coef_i * w_i ;  advances p past the encoded LC   (one thread)
 __device__ __forceinline__ Fr eval_lc(const ProgView& pv, const Fr* __restrict__ W, uint32_t& p) {
     const uint32_t n = pv.code[p], ci = pv.code[p + 1];
     p += 2;
-    Fr acc = ci != 0xffffffffu ? pv.consts[ci].from_mont() : Fr::zero();
+    Fr acc = ci != 0xffffffffu ? pv.consts_can[ci] : Fr::zero();
+    if (n == 0) return acc;
+    // one term of lookahead: the next wire is in flight while this one is folded in
+    uint32_t w = pv.code[p], c = pv.code[p + 1];
+    Fr v = W[w];
     for (uint32_t t = 0; t < n; t++) {
-        const uint32_t w = pv.code[p], c = pv.code[p + 1];
+        const uint32_t c_cur = c;
+        const Fr v_cur = v;
         p += 2;
-        const Fr v = W[w];
-        if (c == 0) acc = acc + v;            // coefficient 1
-        else if (c == 1) acc = acc - v;       // coefficient -1
-        else if (!v.is_zero()) acc = acc + pv.consts[c] * v;  // Montgomery const x canonical wire = canonical
+        if (t + 1 < n) {
+            w = pv.code[p];
+            c = pv.code[p + 1];
+            v = W[w];
+        }
+        lc_term(pv, acc, c_cur, v_cur);
     }
     return acc;
 }
 
+// the same LC evaluated by a whole warp: lane j folds terms j, j+32, ...; butterfly sum over the lanes.
+// Every lane returns the value.
+__device__ __forceinline__ Fr eval_lc_warp(const ProgView& pv, const Fr* __restrict__ W, uint32_t& p, uint32_t lane) {
+    const uint32_t n = pv.code[p], ci = pv.code[p + 1];
+    p += 2;
+    Fr acc = (ci != 0xffffffffu && lane == 0) ? pv.consts_can[ci] : Fr::zero();
+    for (uint32_t t = lane; t < n; t += 32) {
+        const uint32_t w = pv.code[p + 2 * t], c = pv.code[p + 2 * t + 1];
+        lc_term(pv, acc, c, W[w]);
+    }
+    p += 2 * n;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        Fr o;
+#pragma unroll
+        for (int i = 0; i < 8; i++) o.v[i] = __shfl_xor_sync(0xffffffffu, acc.v[i], off);
+        acc = acc + o;
+    }
+    return acc;
+}
+
+// a * b for canonical operands, canonical result
+__device__ __forceinline__ Fr mul_canonical(const Fr& a, const Fr& b) {
+    if (a.is_zero() || b.is_zero()) return Fr::zero();
+    const bool sa = fits_u32(a), sb = fits_u32(b);
+    if (sa && a.v[0] == 1) return b;
+    if (sb && b.v[0] == 1) return a;
+    if (sa && sb) {  // bytes, words, positions: the product fits 64 bits, far below r
+        const uint64_t pr = (uint64_t)a.v[0] * b.v[0];
+        Fr o = Fr::zero();
+        o.v[0] = (uint32_t)pr;
+        o.v[1] = (uint32_t)(pr >> 32);
+        return o;
+    }
+    return (a * b) * Fr::r2();
+}
+
 __device__ __forceinline__ Fr inv_or_zero(const ProgView& pv, const Fr& v) {
     if (v.is_zero()) return v;
-    uint32_t hi = 0;
-#pragma unroll
-    for (int i = 1; i < 8; i++) hi |= v.v[i];
-    if (hi == 0 && v.v[0] <= NZ_INV_TAB) return pv.invtab[v.v[0]];
+    if (fits_u32(v) && v.v[0] <= NZ_INV_TAB) return pv.invtab[v.v[0]];
     const Fr m = v.neg();
-    hi = 0;
-#pragma unroll
-    for (int i = 1; i < 8; i++) hi |= m.v[i];
-    if (hi == 0 && m.v[0] <= NZ_INV_TAB) return pv.invtab[m.v[0]].neg();  // 1/(-k) = -(1/k)
+    if (fits_u32(m) && m.v[0] <= NZ_INV_TAB) return pv.invtab[m.v[0]].neg();  // 1/(-k) = -(1/k)
     return v.to_mont().inv().from_mont();
 }
 
-__global__ void __launch_bounds__(256) k_witness(ProgView pv, const Fr* __restrict__ inputs, Fr* __restrict__ wires,
-                                                 int32_t* __restrict__ status, uint32_t B) {
+constexpr uint32_t WIT_THREADS = 512;
+
+// Executes instruction i.  WARP: all 32 lanes cooperate on its LCs (lane 0 commits); else one thread.
+template <bool WARP>
+__device__ __forceinline__ bool exec_instr(const ProgView& pv, Fr* __restrict__ W, uint32_t i, uint32_t lane) {
+    uint32_t p = pv.ioff[i];
+    const uint32_t op = pv.code[p];
+    auto LC = [&](uint32_t& q) { return WARP ? eval_lc_warp(pv, W, q, lane) : eval_lc(pv, W, q); };
+    const bool commit = !WARP || lane == 0;
+    if (op == OP_LIN) {
+        const uint32_t dst = pv.code[p + 1];
+        p += 2;
+        const Fr v = LC(p);
+        if (commit) W[dst] = v;
+    } else if (op == OP_MUL) {
+        const uint32_t dst = pv.code[p + 1];
+        p += 2;
+        const Fr a = LC(p);
+        const Fr b = LC(p);
+        const Fr c = LC(p);
+        if (commit) W[dst] = mul_canonical(a, b) + c;
+    } else if (op == OP_BITS) {
+        const uint32_t dst = pv.code[p + 1], src = pv.code[p + 2], n = pv.code[p + 3];
+        const Fr v = W[src];
+        for (uint32_t k = WARP ? lane : 0; k < n; k += WARP ? 32 : 1) {
+            Fr bit = Fr::zero();
+            bit.v[0] = k < 256 ? (v.v[k >> 5] >> (k & 31)) & 1u : 0u;
+            W[dst + k] = bit;
+        }
+    } else if (op == OP_INV) {
+        if (commit) W[pv.code[p + 1]] = inv_or_zero(pv, W[pv.code[p + 2]]);
+    } else {  // OP_ASSERT
+        p += 1;
+        const Fr a = LC(p);
+        const Fr b = LC(p);
+        const Fr c = LC(p);
+        if (commit && mul_canonical(a, b) != c) return true;
+    }
+    return false;
+}
+
+// One CTA per pass.  Within a level the host has put the "long" instructions (many LC terms, or wide bit
+// decompositions) first: those run one per warp, the rest one per thread.
+__global__ void __launch_bounds__(WIT_THREADS) k_witness(ProgView pv, const Fr* __restrict__ inputs, Fr* __restrict__ wires,
+                                                         int32_t* __restrict__ status, uint32_t B) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = WIT_THREADS / 32;
     for (uint32_t pass = blockIdx.x; pass < B; pass += gridDim.x) {
         Fr* W = wires + (size_t)pass * pv.n_total;
         const Fr* in = inputs + (size_t)pass * pv.n_in;
@@ -83,45 +186,20 @@ __global__ void __launch_bounds__(256) k_witness(ProgView pv, const Fr* __restri
         }
         __syncthreads();
         bool failed = false;
+        uint32_t lo = pv.lstart[0], hi = pv.n_levels ? pv.lstart[1] : 0, nl = pv.n_levels ? pv.nlong[0] : 0;
         for (uint32_t l = 0; l < pv.n_levels; l++) {
-            const uint32_t lo = pv.lstart[l], hi = pv.lstart[l + 1];
-            for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-                uint32_t p = pv.ioff[i];
-                const uint32_t op = pv.code[p];
-                if (op == OP_LIN) {
-                    const uint32_t dst = pv.code[p + 1];
-                    p += 2;
-                    W[dst] = eval_lc(pv, W, p);
-                } else if (op == OP_MUL) {
-                    const uint32_t dst = pv.code[p + 1];
-                    p += 2;
-                    const Fr a = eval_lc(pv, W, p);
-                    const Fr b = eval_lc(pv, W, p);
-                    const Fr c = eval_lc(pv, W, p);
-                    Fr ab = Fr::zero();
-                    if (!a.is_zero() && !b.is_zero()) ab = (a * b) * Fr::r2();
-                    W[dst] = ab + c;
-                } else if (op == OP_BITS) {
-                    const uint32_t dst = pv.code[p + 1], src = pv.code[p + 2], n = pv.code[p + 3];
-                    const Fr v = W[src];
-                    for (uint32_t k = 0; k < n; k++) {
-                        Fr bit = Fr::zero();
-                        bit.v[0] = k < 256 ? (v.v[k >> 5] >> (k & 31)) & 1u : 0u;
-                        W[dst + k] = bit;
-                    }
-                } else if (op == OP_INV) {
-                    W[pv.code[p + 1]] = inv_or_zero(pv, W[pv.code[p + 2]]);
-                } else {  // OP_ASSERT
-                    p += 1;
-                    const Fr a = eval_lc(pv, W, p);
-                    const Fr b = eval_lc(pv, W, p);
-                    const Fr c = eval_lc(pv, W, p);
-                    Fr ab = Fr::zero();
-                    if (!a.is_zero() && !b.is_zero()) ab = (a * b) * Fr::r2();
-                    if (ab != c) failed = true;
-                }
+            // next level's bounds are fetched while this one executes
+            uint32_t hi_n = 0, nl_n = 0;
+            if (l + 1 < pv.n_levels) {
+                hi_n = pv.lstart[l + 2];
+                nl_n = pv.nlong[l + 1];
             }
+            for (uint32_t i = lo + warp; i < lo + nl; i += n_warps) failed |= exec_instr<true>(pv, W, i, lane);
+            for (uint32_t i = lo + nl + threadIdx.x; i < hi; i += WIT_THREADS) failed |= exec_instr<false>(pv, W, i, lane);
             __syncthreads();
+            lo = hi;
+            hi = hi_n;
+            nl = nl_n;
         }
         if (failed) atomicExch(&status[pass], NZCB_E_ASSERT);
         __syncthreads();
@@ -148,6 +226,8 @@ extern "C" void nzcb_circuit_free(nzcb_circuit* c) {
         cudaStreamSynchronize(c->ctx->stream);
     }
     cudaFree(c->d_consts);
+    cudaFree(c->d_consts_can);
+    cudaFree(c->d_nlong);
     cudaFree(c->d_ioff);
     cudaFree(c->d_lstart);
     cudaFree(c->d_code);
@@ -194,14 +274,16 @@ extern "C" int32_t nzcb_circuit_load(nzcb_ctx* ctx, const uint8_t* data, size_t 
     const uint8_t* p_ioff = p_consts + (size_t)c->n_consts * 32;
     const uint8_t* p_lstart = p_ioff + (size_t)c->n_instr * 4;
     const uint8_t* p_code = p_lstart + ((size_t)c->n_levels + 1) * 4;
-    // validate once on the host so the kernel can trust every index
+    // validate once on the host so the kernel can trust every index; measure every instruction
+    std::vector<uint32_t> ioff_sorted(c->n_instr), nlong(std::max<uint32_t>(1, c->n_levels), 0);
     {
-        std::vector<uint32_t> code(c->n_code), ioff(c->n_instr), ls(c->n_levels + 1);
+        std::vector<uint32_t> code(c->n_code), ioff(c->n_instr), ls(c->n_levels + 1), weight(c->n_instr, 0);
         memcpy(code.data(), p_code, (size_t)c->n_code * 4);
         memcpy(ioff.data(), p_ioff, (size_t)c->n_instr * 4);
         memcpy(ls.data(), p_lstart, ((size_t)c->n_levels + 1) * 4);
         bool ok = ls[0] == 0 && ls[c->n_levels] == c->n_instr;
         for (uint32_t l = 0; ok && l < c->n_levels; l++) ok = ls[l] <= ls[l + 1];
+        uint32_t cur_weight = 0;  // longest LC of the instruction being checked (or its bit count)
         auto lc_ok = [&](uint32_t& p) {
             if (p + 2 > c->n_code) return false;
             const uint32_t n = code[p], ci = code[p + 1];
@@ -210,37 +292,58 @@ extern "C" int32_t nzcb_circuit_load(nzcb_ctx* ctx, const uint8_t* data, size_t 
             if ((uint64_t)p + 2ull * n > c->n_code) return false;
             for (uint32_t t = 0; t < n; t++, p += 2)
                 if (code[p] >= c->n_total || code[p + 1] >= c->n_consts) return false;
+            cur_weight = std::max(cur_weight, n);
             return true;
         };
         for (uint32_t i = 0; ok && i < c->n_instr; i++) {
             uint32_t p = ioff[i];
             if (p + 1 > c->n_code) { ok = false; break; }
             const uint32_t op = code[p];
+            cur_weight = 0;
             if (op == OP_LIN) {
                 ok = p + 2 <= c->n_code && code[p + 1] < c->n_total; p += 2; ok = ok && lc_ok(p);
             } else if (op == OP_MUL) {
                 ok = p + 2 <= c->n_code && code[p + 1] < c->n_total; p += 2; ok = ok && lc_ok(p) && lc_ok(p) && lc_ok(p);
             } else if (op == OP_BITS) {
                 ok = p + 4 <= c->n_code && code[p + 2] < c->n_total && (uint64_t)code[p + 1] + code[p + 3] <= c->n_total;
+                if (ok) cur_weight = code[p + 3];
             } else if (op == OP_INV) {
                 ok = p + 3 <= c->n_code && code[p + 1] < c->n_total && code[p + 2] < c->n_total;
             } else if (op == OP_ASSERT) {
                 p += 1; ok = lc_ok(p) && lc_ok(p) && lc_ok(p);
             } else ok = false;
+            weight[i] = cur_weight;
         }
         if (!ok) {
             delete c;
             return ctx->fail(NZCB_E_INVALID, "witness program: malformed instruction stream");
         }
+        // inside each level: long instructions (one warp each) first, by decreasing length
+        std::vector<uint32_t> order;
+        for (uint32_t l = 0; l < c->n_levels; l++) {
+            order.clear();
+            for (uint32_t i = ls[l]; i < ls[l + 1]; i++) order.push_back(i);
+            std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return weight[a] > weight[b]; });
+            uint32_t nl = 0;
+            for (size_t k = 0; k < order.size(); k++) {
+                ioff_sorted[ls[l] + k] = ioff[order[k]];
+                if (weight[order[k]] > NZ_LONG_LC) nl++;
+            }
+            nlong[l] = nl;
+        }
     }
     WC_CUDA(cudaSetDevice(ctx->device));
     WC_CUDA(cudaMalloc(&c->d_consts, (size_t)c->n_consts * 32));
+    WC_CUDA(cudaMalloc(&c->d_consts_can, (size_t)c->n_consts * 32));
+    WC_CUDA(cudaMalloc(&c->d_nlong, nlong.size() * 4));
+    WC_CUDA(cudaMemcpyAsync(c->d_consts_can, p_consts, (size_t)c->n_consts * 32, cudaMemcpyHostToDevice, ctx->stream));
+    WC_CUDA(cudaMemcpyAsync(c->d_nlong, nlong.data(), nlong.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
     WC_CUDA(cudaMalloc(&c->d_ioff, std::max<size_t>(4, (size_t)c->n_instr * 4)));
     WC_CUDA(cudaMalloc(&c->d_lstart, ((size_t)c->n_levels + 1) * 4));
     WC_CUDA(cudaMalloc(&c->d_code, std::max<size_t>(4, (size_t)c->n_code * 4)));
     WC_CUDA(cudaMalloc(&c->d_invtab, (NZ_INV_TAB + 1) * sizeof(Fr)));
     WC_CUDA(cudaMemcpyAsync(c->d_consts, p_consts, (size_t)c->n_consts * 32, cudaMemcpyHostToDevice, ctx->stream));
-    WC_CUDA(cudaMemcpyAsync(c->d_ioff, p_ioff, (size_t)c->n_instr * 4, cudaMemcpyHostToDevice, ctx->stream));
+    WC_CUDA(cudaMemcpyAsync(c->d_ioff, ioff_sorted.data(), (size_t)c->n_instr * 4, cudaMemcpyHostToDevice, ctx->stream));
     WC_CUDA(cudaMemcpyAsync(c->d_lstart, p_lstart, ((size_t)c->n_levels + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
     WC_CUDA(cudaMemcpyAsync(c->d_code, p_code, (size_t)c->n_code * 4, cudaMemcpyHostToDevice, ctx->stream));
     k_consts_to_mont<<<div_up(c->n_consts, 256), 256, 0, ctx->stream>>>(c->d_consts, c->n_consts);
@@ -256,11 +359,12 @@ namespace nzcb {
 // runs B passes; wires for pass i start at *d_wires + i * n_total (canonical LE).  Asynchronous on ctx->stream.
 int witness_dev(nzcb_ctx* ctx, const nzcb_circuit* c, const Fr* d_inputs, size_t B, Fr* d_wires, int32_t* d_status) {
     ProgView pv;
-    pv.consts = c->d_consts; pv.ioff = c->d_ioff; pv.lstart = c->d_lstart; pv.code = c->d_code; pv.invtab = c->d_invtab;
+    pv.consts = c->d_consts; pv.consts_can = c->d_consts_can; pv.ioff = c->d_ioff; pv.lstart = c->d_lstart;
+    pv.nlong = c->d_nlong; pv.code = c->d_code; pv.invtab = c->d_invtab;
     pv.n_total = c->n_total; pv.n_out = c->n_out; pv.n_in = c->n_in; pv.n_levels = c->n_levels;
     NZ_CUDA(ctx, cudaMemsetAsync(d_status, 0, B * sizeof(int32_t), ctx->stream));
     const uint32_t grid = (uint32_t)std::min<size_t>(B, (size_t)ctx->sm_count * 8);
-    NZ_LAUNCH(ctx, k_witness, grid, 256, 0, pv, d_inputs, d_wires, d_status, (uint32_t)B);
+    NZ_LAUNCH(ctx, k_witness, grid, WIT_THREADS, 0, pv, d_inputs, d_wires, d_status, (uint32_t)B);
     return 0;
 }
 uint32_t circuit_n_total(const nzcb_circuit* c) { return c->n_total; }
