@@ -69,6 +69,8 @@ float nzcb_last_device_ms(const nzcb_ctx* ctx);
  * 1 = IMAD.WIDE.U32, 2 = Fr Montgomery multiply, 3 = Fq multiply, 4 = IMAD.HI.U32,
  * 5 = Fr multiply, portable CIOS variant; result in ops/s */
 int32_t nzcb_microbench(nzcb_ctx* ctx, int32_t kind, uint32_t iters, uint32_t blocks_per_sm, double* ops_per_s);
+/* mixed-addition (XYZZ += affine, the body of the MSM accumulation) loop variants; result in additions/s */
+int32_t nzcb_microbench_madd(nzcb_ctx* ctx, int32_t variant, uint32_t iters, uint32_t log_table, double* madds_per_s);
 /* device self-test: carry-chain multiply vs portable CIOS on n random operand pairs x 16 */
 int32_t nzcb_selftest_mul(nzcb_ctx* ctx, uint32_t n, uint64_t* mismatches);
 

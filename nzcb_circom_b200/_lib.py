@@ -45,6 +45,7 @@ SIGNATURES = {
     "nzcb_launch_count": (ctypes.c_uint64, [_vp]),
     "nzcb_last_device_ms": (ctypes.c_float, [_vp]),
     "nzcb_microbench": (_i32, [_vp, _i32, _u32, _u32, ctypes.POINTER(ctypes.c_double)]),
+    "nzcb_microbench_madd": (_i32, [_vp, _i32, _u32, _u32, ctypes.POINTER(ctypes.c_double)]),
     "nzcb_selftest_mul": (_i32, [_vp, _u32, ctypes.POINTER(ctypes.c_uint64)]),
     "nzcb_ntt_fr": (_i32, [_vp, _vp, _u32, _i32]),
     "nzcb_msm_g1": (_i32, [_vp, _vp, _vp, _sz, _vp]),
@@ -133,6 +134,11 @@ class Context:
     def microbench(self, kind, iters=2000, blocks_per_sm=8):
         v = ctypes.c_double()
         self.check(self.lib.nzcb_microbench(self.h, kind, iters, blocks_per_sm, ctypes.byref(v)))
+        return v.value
+
+    def microbench_madd(self, variant, iters=2000, log_table=10):
+        v = ctypes.c_double()
+        self.check(self.lib.nzcb_microbench_madd(self.h, variant, iters, log_table, ctypes.byref(v)))
         return v.value
 
     def profile(self, enable=True):

@@ -46,10 +46,37 @@ extern "C" int32_t nzcb_ctx_create(int32_t device_id, nzcb_ctx** out) {
     return 0;
 }
 
+namespace nzcb {
+nzcb_ctx* ctx_lane(nzcb_ctx* root, int i) {
+    if (i < 0 || i >= 16) return nullptr;
+    std::lock_guard<std::mutex> g(root->mu);
+    while ((int)root->lanes.size() <= i) {
+        nzcb_ctx* l = new nzcb_ctx();
+        l->parent = root;
+        l->device = root->device;
+        l->sm_count = root->sm_count;
+        cudaSetDevice(root->device);
+        if (cudaStreamCreateWithFlags(&l->stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreate(&l->ev0) != cudaSuccess || cudaEventCreate(&l->ev1) != cudaSuccess) {
+            cudaGetLastError();
+            if (l->stream) cudaStreamDestroy(l->stream);
+            if (l->ev0) cudaEventDestroy(l->ev0);
+            if (l->ev1) cudaEventDestroy(l->ev1);
+            delete l;
+            return nullptr;
+        }
+        root->lanes.push_back(l);
+    }
+    return root->lanes[i];
+}
+}  // namespace nzcb
+
 extern "C" void nzcb_ctx_free(nzcb_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (nzcb_ctx* l : ctx->lanes) nzcb_ctx_free(l);
+    ctx->lanes.clear();
     for (auto& kv : ctx->twiddles) cudaFree(kv.second);
     for (auto& kv : ctx->scratch)
         if (kv.second.first) cudaFree(kv.second.first);
@@ -69,6 +96,7 @@ extern "C" int32_t nzcb_profile(nzcb_ctx* ctx, int32_t enable) {
     ctx->prof_on = enable != 0;
     ctx->prof_used = 0;
     ctx->prof_modmul = 0;
+    for (nzcb_ctx* l : ctx->lanes) nzcb_profile(l, enable);
     return 0;
 }
 extern "C" int32_t nzcb_profile_read(nzcb_ctx* ctx, uint64_t* launches, double* total_ms, double* alg_modmul) {
@@ -80,16 +108,31 @@ extern "C" int32_t nzcb_profile_read(nzcb_ctx* ctx, uint64_t* launches, double* 
         cudaEventElapsedTime(&t, ctx->prof_ev[i].first, ctx->prof_ev[i].second);
         ms += t;
     }
-    if (launches) *launches = ctx->prof_used;
-    if (total_ms) *total_ms = ms;
-    if (alg_modmul) *alg_modmul = ctx->prof_modmul;
+    uint64_t n = ctx->prof_used;
+    double mm = ctx->prof_modmul;
     ctx->prof_used = 0;
     ctx->prof_modmul = 0;
+    for (nzcb_ctx* l : ctx->lanes) {
+        uint64_t ln = 0;
+        double lms = 0, lmm = 0;
+        nzcb_profile_read(l, &ln, &lms, &lmm);
+        n += ln;
+        ms += lms;
+        mm += lmm;
+    }
+    if (launches) *launches = n;
+    if (total_ms) *total_ms = ms;
+    if (alg_modmul) *alg_modmul = mm;
     return 0;
 }
 
 extern "C" const char* nzcb_last_error(const nzcb_ctx* ctx) { return ctx ? ctx->err : g_noctx_err; }
-extern "C" uint64_t nzcb_launch_count(const nzcb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" uint64_t nzcb_launch_count(const nzcb_ctx* ctx) {
+    if (!ctx) return 0;
+    uint64_t n = ctx->launches;
+    for (const nzcb_ctx* l : ctx->lanes) n += l->launches;
+    return n;
+}
 extern "C" float nzcb_last_device_ms(const nzcb_ctx* ctx) { return ctx ? ctx->last_ms : 0.f; }
 
 extern "C" int32_t nzcb_dev_alloc(nzcb_ctx* ctx, size_t bytes, void** dptr) {

@@ -7,6 +7,7 @@
 #include <stdarg.h>
 #include <string.h>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 #include "../../include/nzcb.h"
@@ -17,7 +18,13 @@ struct NttTables;
 struct MsmWorkspace;
 }  // namespace nzcb
 
+// One ctx = one GPU.  The root ctx owns the twiddle tables; "lanes" are child contexts (own stream, scratch
+// arenas, events, error text) that the batch entry points drive from one host thread each, so that the
+// latency-bound tails of one proof overlap the throughput-bound kernels of another.
 struct nzcb_ctx {
+    nzcb_ctx* parent = nullptr;          // non-null for a lane
+    std::vector<nzcb_ctx*> lanes;        // root only
+    std::mutex mu;                       // root only: guards the twiddle map
     int device = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
@@ -35,6 +42,7 @@ struct nzcb_ctx {
     // grow-only scratch arenas keyed by name, so steady-state proving never mallocs
     std::map<std::string, std::pair<void*, size_t>> scratch;
 
+    nzcb_ctx* root() { return parent ? parent : this; }
     int fail(int code, const char* fmt, ...) {
         va_list ap;
         va_start(ap, fmt);
@@ -94,6 +102,8 @@ namespace nzcb {
 static inline unsigned div_up(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 
 // --- internal device-level entry points (all asynchronous on ctx->stream) ---
+// api.cu : lane `i` of a root ctx (created on first use)
+nzcb_ctx* ctx_lane(nzcb_ctx* root, int i);
 // ntt.cu
 int ntt_dev(nzcb_ctx* ctx, Fr* d_data, uint32_t log_n, bool inverse);
 // msm.cu : result left in d_out (one G1XYZZ) ; scalars 8 x u32 each.  One-shot bases (window mode).

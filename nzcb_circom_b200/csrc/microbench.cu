@@ -80,6 +80,61 @@ __global__ void __launch_bounds__(256) k_microbench(uint32_t* out, uint32_t iter
 }
 
 
+// ---- mixed-addition loop variants (the body of k_msm_accum): what limits it on the integer pipe? ------------
+struct MulInline {
+    static __device__ __forceinline__ Fq mul(const Fq& a, const Fq& b) { return a * b; }
+};
+__device__ __noinline__ Fq fq_mul_call(Fq a, Fq b) { return a * b; }
+struct MulCall {
+    static __device__ __forceinline__ Fq mul(const Fq& a, const Fq& b) { return fq_mul_call(a, b); }
+};
+template <class M>
+__device__ __forceinline__ void madd_v(G1XYZZ& r, const G1Affine& b) {
+    if (b.is_inf()) return;
+    if (r.is_inf()) {
+        r = G1XYZZ::from_affine(b);
+        return;
+    }
+    const Fq U2 = M::mul(b.x, r.ZZ), S2 = M::mul(b.y, r.ZZZ);
+    const Fq Pp = U2 - r.X, Rr = S2 - r.Y;
+    if (Pp.is_zero()) {
+        r = Rr.is_zero() ? G1XYZZ::from_affine(b).dbl() : G1XYZZ::inf();
+        return;
+    }
+    const Fq PP = M::mul(Pp, Pp), PPP = M::mul(Pp, PP), Q = M::mul(r.X, PP);
+    const Fq X3 = M::mul(Rr, Rr) - PPP - Q.dbl();
+    r.Y = M::mul(Rr, Q - X3) - M::mul(r.Y, PPP);
+    r.X = X3;
+    r.ZZ = M::mul(r.ZZ, PP);
+    r.ZZZ = M::mul(r.ZZZ, PPP);
+}
+template <class M, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) k_madd_bench(const G1Affine* __restrict__ tab, uint32_t tab_mask,
+                                                              uint32_t iters, uint32_t* __restrict__ out) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    G1XYZZ acc = G1XYZZ::from_affine(tab[tid & tab_mask]);
+    uint32_t idx = tid * 2654435761u;
+    G1Affine p = tab[idx & tab_mask];
+    for (uint32_t i = 0; i < iters; i++) {
+        const G1Affine cur = p;
+        idx = idx * 1664525u + 1013904223u;
+        p = tab[(idx >> 8) & tab_mask];
+        madd_v<M>(acc, cur);
+    }
+    uint32_t x = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) x ^= acc.X.v[k] ^ acc.Y.v[k] ^ acc.ZZ.v[k] ^ acc.ZZZ.v[k];
+    out[tid] = x;
+}
+__global__ void k_madd_table(G1Affine* tab, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    G1Affine g;
+    g.x = Fq::from_u64(1);
+    g.y = Fq::from_u64(2);
+    tab[i] = g1_mul_small(G1XYZZ::from_affine(g), 3 + i).to_affine();
+}
+
 // device self-test: the carry-chain multiply must agree bit-for-bit with the portable CIOS
 template <class F>
 __global__ void k_selftest_mul(uint32_t n, uint32_t seed, unsigned long long* mismatches) {
@@ -147,5 +202,39 @@ extern "C" int32_t nzcb_microbench(nzcb_ctx* ctx, int32_t kind, uint32_t iters, 
     cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1);
     const double per_thread = (kind <= 1 || kind == 4) ? 64.0 * iters : 4.0 * iters;
     *ops_per_s = per_thread * grid * 256.0 / (ctx->last_ms * 1e-3);
+    return 0;
+}
+
+
+// mixed-addition loop: variant 0 = inlined multiplies (128 thr, 4 CTA/SM), 1 = multiply as a call, 2 = inlined,
+// 128 thr x 3 CTA/SM (168 regs), 3 = inlined 256 thr x 2, 4 = call 256 x 3.  Result: mixed additions per second.
+extern "C" int32_t nzcb_microbench_madd(nzcb_ctx* ctx, int32_t variant, uint32_t iters, uint32_t log_table,
+                                        double* madds_per_s) {
+    if (!ctx || !madds_per_s || variant < 0 || variant > 4 || log_table > 24) return NZCB_E_INVALID;
+    const uint32_t n = 1u << log_table;
+    G1Affine* tab = (G1Affine*)ctx->scratch_get("madd_tab", (size_t)n * sizeof(G1Affine));
+    if (!tab) return ctx->fail(NZCB_E_NOMEM, "microbench: out of memory");
+    NZ_LAUNCH(ctx, k_madd_table, div_up(n, 128), 128, 0, tab, n);
+    uint32_t threads = 128, bps = 4;
+    if (variant == 2) bps = 3;
+    if (variant == 3) { threads = 256; bps = 2; }
+    if (variant == 4) { threads = 256; bps = 3; }
+    const uint32_t grid = (uint32_t)ctx->sm_count * bps;
+    uint32_t* d = (uint32_t*)ctx->scratch_get("microbench", (size_t)grid * threads * 4);
+    if (!d) return ctx->fail(NZCB_E_NOMEM, "microbench: out of memory");
+    for (int rep = 0; rep < 2; rep++) {
+        NZ_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+        switch (variant) {
+            case 0: NZ_LAUNCH(ctx, (k_madd_bench<MulInline, 128, 4>), grid, threads, 0, tab, n - 1, iters, d); break;
+            case 1: NZ_LAUNCH(ctx, (k_madd_bench<MulCall, 128, 4>), grid, threads, 0, tab, n - 1, iters, d); break;
+            case 2: NZ_LAUNCH(ctx, (k_madd_bench<MulInline, 128, 3>), grid, threads, 0, tab, n - 1, iters, d); break;
+            case 3: NZ_LAUNCH(ctx, (k_madd_bench<MulInline, 256, 2>), grid, threads, 0, tab, n - 1, iters, d); break;
+            default: NZ_LAUNCH(ctx, (k_madd_bench<MulCall, 256, 3>), grid, threads, 0, tab, n - 1, iters, d); break;
+        }
+        NZ_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+        NZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1);
+    *madds_per_s = (double)iters * grid * threads / (ctx->last_ms * 1e-3);
     return 0;
 }

@@ -231,74 +231,92 @@ static int scan_excl(nzcb_ctx* ctx, const uint32_t* counts, uint32_t* offsets, s
     return 0;
 }
 
-// ---- step 4: accumulation over equal-length segments ----------------------------------------
-// Thread t owns sorted[t*L, (t+1)*L), L = max(LMIN, ceil(E / threads)) with E = offsets[n_keys] read on the
-// device (no host round trip).  Output per thread: two (key, partial) slots; every other bucket it meets lies
-// wholly inside its segment and is written straight to buckets[].
-constexpr uint32_t ACC_THREADS = 128, ACC_LMIN = 8;
+// ---- step 4: accumulation over equal-length chunks -------------------------------------------
+// The sorted list is cut into chunks of L consecutive entries (L chosen on the host from the upper bound of the
+// entry count, so the (key, partial) list has a host-known size); a tile = ACC_THREADS chunks.  The grid is
+// persistent -- one CTA per resident slot -- and CTAs draw tiles from an atomic counter, so the kernel keeps its
+// balance whatever shares the GPU with it (other lanes' kernels, the witness program).
+// Per chunk: two (key, partial) slots for its first and last bucket (possibly shared with the neighbours);
+// every other bucket it meets lies wholly inside the chunk and is written straight to buckets[].
+constexpr uint32_t ACC_THREADS = 128, ACC_LMIN = 8, ACC_LMAX = 64;
 
-__global__ void __launch_bounds__(ACC_THREADS, 4)
-    k_msm_accum(const G1Affine* __restrict__ bases, const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ offsets,
-                uint32_t n_keys, G1XYZZ* __restrict__ buckets, uint32_t* __restrict__ pkeys, G1XYZZ* __restrict__ pvals) {
-    const uint32_t t = blockIdx.x * ACC_THREADS + threadIdx.x;
-    const uint32_t T = gridDim.x * ACC_THREADS;
+// bucket holding the first entry of every chunk (binary search in the offsets, off the hot kernel's critical path)
+__global__ void __launch_bounds__(256) k_msm_chunk_buckets(const uint32_t* __restrict__ offsets, uint32_t n_keys, uint32_t L,
+                                                           uint32_t* __restrict__ chunk_bucket, uint32_t max_chunks) {
+    const uint32_t ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= max_chunks) return;
     const uint32_t E = offsets[n_keys];
-    uint32_t L = (E + T - 1) / T;
-    if (L < ACC_LMIN) L = ACC_LMIN;
-    const uint64_t lo64 = (uint64_t)t * L;
-    if (lo64 >= E) {
-        pkeys[2 * t] = KEY_NONE;
-        pkeys[2 * t + 1] = KEY_NONE;
-        return;
-    }
-    const uint32_t lo = (uint32_t)lo64;
-    const uint32_t hi = (uint64_t)lo + L < E ? lo + L : E;
-    // bucket of entry lo: the largest b with offsets[b] <= lo  (offsets[n_keys] = E > lo)
+    const uint64_t lo = (uint64_t)ch * L;
+    if (lo >= E) return;
+    // the largest b with offsets[b] <= lo  (offsets[n_keys] = E > lo)
     uint32_t b = 0, z = n_keys;
     while (z - b > 1) {
         const uint32_t m = (b + z) >> 1;
-        if (offsets[m] <= lo) b = m;
+        if (offsets[m] <= (uint32_t)lo) b = m;
         else z = m;
     }
-    uint32_t next = offsets[b + 1];
-    G1XYZZ acc = G1XYZZ::inf();
-    bool first = true;
-    uint32_t e = sorted[lo];
-    G1Affine p = bases[e & 0x7fffffffu];
-    for (uint32_t k = lo; k < hi; k++) {
-        // prefetch the next point while this one is added
-        const uint32_t e_cur = e;
-        const G1Affine p_cur = p;
-        if (k + 1 < hi) {
-            e = sorted[k + 1];
-            p = bases[e & 0x7fffffffu];
-        }
-        if (k == next) {  // bucket boundary: flush
-            if (first) {
-                pkeys[2 * t] = b;
-                pvals[2 * t] = acc;
-                first = false;
-            } else {
-                buckets[b] = acc;
+    chunk_bucket[ch] = b;
+}
+
+__global__ void __launch_bounds__(ACC_THREADS, 4)
+    k_msm_accum(const G1Affine* __restrict__ bases, const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ offsets,
+                uint32_t n_keys, uint32_t L, const uint32_t* __restrict__ chunk_bucket, uint32_t* __restrict__ tile_counter,
+                G1XYZZ* __restrict__ buckets, uint32_t* __restrict__ pkeys, G1XYZZ* __restrict__ pvals) {
+    __shared__ uint32_t s_tile;
+    const uint32_t E = offsets[n_keys];
+    const uint32_t n_chunks = (uint32_t)(((uint64_t)E + L - 1) / L);
+    const uint32_t n_tiles = (n_chunks + ACC_THREADS - 1) / ACC_THREADS;
+    for (;;) {
+        if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
+        __syncthreads();
+        const uint32_t tile = s_tile;
+        __syncthreads();
+        if (tile >= n_tiles) break;
+        const uint32_t t = tile * ACC_THREADS + threadIdx.x;  // chunk id
+        if (t >= n_chunks) continue;
+        const uint32_t lo = t * L;  // < E <= 2^32 - 1
+        const uint32_t hi = (uint64_t)lo + L < E ? lo + L : E;
+        uint32_t b = chunk_bucket[t];
+        uint32_t next = offsets[b + 1];
+        G1XYZZ acc = G1XYZZ::inf();
+        bool first = true;
+        uint32_t e = sorted[lo];
+        G1Affine p = bases[e & 0x7fffffffu];
+        for (uint32_t k = lo; k < hi; k++) {
+            // prefetch the next point while this one is added
+            const uint32_t e_cur = e;
+            const G1Affine p_cur = p;
+            if (k + 1 < hi) {
+                e = sorted[k + 1];
+                p = bases[e & 0x7fffffffu];
             }
-            acc = G1XYZZ::inf();
-            do {
-                b++;
-                next = offsets[b + 1];
-            } while (next == k);
+            if (k == next) {  // bucket boundary: flush
+                if (first) {
+                    pkeys[2 * t] = b;
+                    pvals[2 * t] = acc;
+                    first = false;
+                } else {
+                    buckets[b] = acc;
+                }
+                acc = G1XYZZ::inf();
+                do {
+                    b++;
+                    next = offsets[b + 1];
+                } while (next == k);
+            }
+            G1Affine q = p_cur;
+            if (e_cur & 0x80000000u) q.y = q.y.neg();  // (0,0) stays (0,0)
+            acc.add_affine(q);
         }
-        G1Affine q = p_cur;
-        if (e_cur & 0x80000000u) q.y = q.y.neg();  // (0,0) stays (0,0)
-        acc.add_affine(q);
-    }
-    if (first) {
-        pkeys[2 * t] = b;
-        pvals[2 * t] = acc;
-        pkeys[2 * t + 1] = b;
-        pvals[2 * t + 1] = G1XYZZ::inf();
-    } else {
-        pkeys[2 * t + 1] = b;
-        pvals[2 * t + 1] = acc;
+        if (first) {
+            pkeys[2 * t] = b;
+            pvals[2 * t] = acc;
+            pkeys[2 * t + 1] = b;
+            pvals[2 * t + 1] = G1XYZZ::inf();
+        } else {
+            pkeys[2 * t + 1] = b;
+            pvals[2 * t + 1] = acc;
+        }
     }
 }
 
@@ -421,19 +439,22 @@ static int msm_run(nzcb_ctx* ctx, const G1Affine* d_bases, const MsmPlan& p, con
     if (n_sum * p.W >= ((size_t)1 << 32) || n_keys >= ((size_t)1 << 31))
         return ctx->fail(NZCB_E_INVALID, "msm: batch too large");
 
-    // accumulation grid: one resident wave
-    static int blocks_per_sm = 0;
-    if (!blocks_per_sm) {
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_msm_accum, ACC_THREADS, 0) != cudaSuccess ||
-            blocks_per_sm < 1)
-            blocks_per_sm = 1;
+    // accumulation grid: persistent, one CTA per resident slot; chunk length from the entry-count upper bound
+    static const int blocks_per_sm = [] {
+        int v = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_msm_accum, ACC_THREADS, 0) != cudaSuccess || v < 1) v = 1;
+        return v;
+    }();
+    const size_t e_max = n_sum * p.W;
+    const uint32_t acc_slots = (uint32_t)ctx->sm_count * (uint32_t)blocks_per_sm;
+    uint32_t L = (uint32_t)std::min<size_t>(ACC_LMAX, std::max<size_t>(ACC_LMIN, e_max / ((size_t)acc_slots * ACC_THREADS * 4)));
+    {
+        const char* env = getenv("NZCB_MSM_CHUNK");
+        if (env && atoi(env) >= 1 && atoi(env) <= 4096) L = (uint32_t)atoi(env);
     }
-    uint32_t acc_blocks = (uint32_t)ctx->sm_count * (uint32_t)blocks_per_sm;
-    {   // never more threads than ceil(max entries / LMIN)
-        const size_t need = (n_sum * p.W + (size_t)ACC_LMIN * ACC_THREADS - 1) / ((size_t)ACC_LMIN * ACC_THREADS);
-        if (need < acc_blocks) acc_blocks = (uint32_t)std::max<size_t>(1, need);
-    }
-    const uint32_t T1 = acc_blocks * ACC_THREADS;
+    const uint32_t max_chunks = (uint32_t)((e_max + L - 1) / L);
+    const uint32_t acc_blocks = std::max<uint32_t>(1, std::min<uint32_t>(acc_slots, div_up(max_chunks, ACC_THREADS)));
+    const uint32_t T1 = max_chunks;  // (key, partial) list: two slots per chunk
 
     uint32_t* counts = (uint32_t*)ctx->scratch_get("msm_counts", (n_keys + 1) * 4);
     uint32_t* offsets = (uint32_t*)ctx->scratch_get("msm_offsets", (n_keys + 1) * 4);
@@ -443,13 +464,16 @@ static int msm_run(nzcb_ctx* ctx, const G1Affine* d_bases, const MsmPlan& p, con
     uint32_t* pk1 = (uint32_t*)ctx->scratch_get("msm_pk1", (size_t)2 * T1 * 4);
     G1XYZZ* pv0 = (G1XYZZ*)ctx->scratch_get("msm_pv0", (size_t)2 * T1 * sizeof(G1XYZZ));
     G1XYZZ* pv1 = (G1XYZZ*)ctx->scratch_get("msm_pv1", (size_t)2 * T1 * sizeof(G1XYZZ));
+    uint32_t* chunk_bucket = (uint32_t*)ctx->scratch_get("msm_chunk_bucket", (size_t)max_chunks * 4 + 4);
+    uint32_t* tile_counter = (uint32_t*)ctx->scratch_get("msm_tile_counter", 256);
     // reduction ping-pong: level 1 output has n_keys / 2^log_S elements
     const size_t red_cap = std::max<size_t>(n_keys / 2, p.G) + 1;
     G1XYZZ* rx0 = (G1XYZZ*)ctx->scratch_get("msm_rx0", red_cap * sizeof(G1XYZZ));
     G1XYZZ* rp0 = (G1XYZZ*)ctx->scratch_get("msm_rp0", red_cap * sizeof(G1XYZZ));
     G1XYZZ* rx1 = (G1XYZZ*)ctx->scratch_get("msm_rx1", red_cap * sizeof(G1XYZZ));
     G1XYZZ* rp1 = (G1XYZZ*)ctx->scratch_get("msm_rp1", red_cap * sizeof(G1XYZZ));
-    if (!counts || !offsets || !sorted || !buckets || !pk0 || !pk1 || !pv0 || !pv1 || !rx0 || !rp0 || !rx1 || !rp1)
+    if (!counts || !offsets || !sorted || !buckets || !pk0 || !pk1 || !pv0 || !pv1 || !rx0 || !rp0 || !rx1 || !rp1 ||
+        !chunk_bucket || !tile_counter)
         return ctx->fail(NZCB_E_NOMEM, "msm: cannot allocate workspace for %zu scalars", n_sum);
 
     // 1-3: sort the point references by bucket
@@ -460,6 +484,9 @@ static int msm_run(nzcb_ctx* ctx, const G1Affine* d_bases, const MsmPlan& p, con
     NZ_CUDA(ctx, cudaMemsetAsync(counts, 0, (n_keys + 1) * 4, ctx->stream));
     NZ_LAUNCH(ctx, k_msm_digits<false>, dgrid, 256, 0, da, counts, offsets, sorted);
     NZ_CUDA(ctx, cudaMemsetAsync(buckets, 0, n_keys * sizeof(G1XYZZ), ctx->stream));  // ZZ = 0: infinity
+    NZ_CUDA(ctx, cudaMemsetAsync(pk0, 0xff, (size_t)2 * T1 * 4, ctx->stream));            // KEY_NONE beyond the last chunk
+    NZ_CUDA(ctx, cudaMemsetAsync(tile_counter, 0, 4, ctx->stream));
+    NZ_LAUNCH(ctx, k_msm_chunk_buckets, div_up(max_chunks, 256), 256, 0, offsets, (uint32_t)n_keys, L, chunk_bucket, max_chunks);
 
     // 4: accumulate
     if (ctx->prof_on) {
@@ -471,7 +498,8 @@ static int msm_run(nzcb_ctx* ctx, const G1Affine* d_bases, const MsmPlan& p, con
         }
         NZ_CUDA(ctx, cudaEventRecord(ctx->prof_ev[ctx->prof_used].first, ctx->stream));
     }
-    NZ_LAUNCH(ctx, k_msm_accum, acc_blocks, ACC_THREADS, 0, d_bases, sorted, offsets, (uint32_t)n_keys, buckets, pk0, pv0);
+    NZ_LAUNCH(ctx, k_msm_accum, acc_blocks, ACC_THREADS, 0, d_bases, sorted, offsets, (uint32_t)n_keys, L, chunk_bucket,
+              tile_counter, buckets, pk0, pv0);
     if (ctx->prof_on) {
         NZ_CUDA(ctx, cudaEventRecord(ctx->prof_ev[ctx->prof_used].second, ctx->stream));
         ctx->prof_used++;
@@ -481,14 +509,14 @@ static int msm_run(nzcb_ctx* ctx, const G1Affine* d_bases, const MsmPlan& p, con
         uint32_t N = 2 * T1;
         uint32_t *ki = pk0, *ko = pk1;
         G1XYZZ *vi = pv0, *vo = pv1;
-        uint32_t L = 8;
+        uint32_t SL = 8;  // list entries per thread at this level
         while (N > 32) {
-            const uint32_t threads = (N + L - 1) / L;
-            NZ_LAUNCH(ctx, k_seg_level, div_up(threads, 128), 128, 0, ki, vi, N, L, buckets, ko, vo, 0);
+            const uint32_t threads = (N + SL - 1) / SL;
+            NZ_LAUNCH(ctx, k_seg_level, div_up(threads, 128), 128, 0, ki, vi, N, SL, buckets, ko, vo, 0);
             N = 2 * threads;
             std::swap(ki, ko);
             std::swap(vi, vo);
-            L = 32;
+            SL = 32;
         }
         NZ_LAUNCH(ctx, k_seg_level, 1, 32, 0, ki, vi, N, N, buckets, ko, vo, 1);
     }

@@ -92,10 +92,13 @@ Fr fr_root_host(uint32_t log_n) {
     return w;
 }
 
+// tables live in the root ctx and are shared by its lanes (built once, complete before anyone reads them)
 int get_twiddles_pub(nzcb_ctx* ctx, uint32_t log_n, bool inverse, const Fr** out) {
+    nzcb_ctx* root = ctx->root();
+    std::lock_guard<std::mutex> g(root->mu);
     const uint32_t key = log_n * 2 + (inverse ? 1 : 0);
-    auto it = ctx->twiddles.find(key);
-    if (it != ctx->twiddles.end()) {
+    auto it = root->twiddles.find(key);
+    if (it != root->twiddles.end()) {
         *out = it->second;
         return 0;
     }
@@ -105,7 +108,8 @@ int get_twiddles_pub(nzcb_ctx* ctx, uint32_t log_n, bool inverse, const Fr** out
     Fr w = fr_root_host(log_n);
     if (inverse) w = w.inv();
     NZ_LAUNCH(ctx, k_twiddle_fill, div_up(half, 256), 256, 0, W, w, half);
-    ctx->twiddles[key] = W;
+    NZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    root->twiddles[key] = W;
     *out = W;
     return 0;
 }

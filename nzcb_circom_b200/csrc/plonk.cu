@@ -12,6 +12,8 @@
 #include "keccak.h"
 #include "poly.cuh"
 #include <algorithm>
+#include <atomic>
+#include <thread>
 
 using namespace nzcb;
 
@@ -897,30 +899,7 @@ extern "C" int32_t nzcb_plonk_prove(nzcb_ctx* ctx, const nzcb_zkey* zk, const ui
     return 0;
 }
 
-extern "C" int32_t nzcb_plonk_prove_batch(nzcb_ctx* ctx, const nzcb_zkey* zk, const uint8_t* const* wtns,
-                                          const size_t* wtns_len, const uint8_t* blinders_le, size_t B, nzcb_proof* out,
-                                          uint8_t* public_le, int32_t* status) {
-    if (!ctx || !zk || !wtns || !wtns_len || !out) return NZCB_E_INVALID;
-    if (zk->ctx != ctx) return ctx->fail(NZCB_E_INVALID, "zkey was loaded on a different context");
-    cudaEventRecord(ctx->ev0, ctx->stream);
-    int32_t first_err = 0;
-    for (size_t i = 0; i < B; i++) {
-        const int rc = prove_one(ctx, zk, wtns[i], wtns_len[i], blinders_le ? blinders_le + i * 9 * 32 : nullptr, out + i,
-                                 public_le ? public_le + i * (size_t)zk->n_public * 32 : nullptr);
-        if (status) status[i] = rc;
-        if (rc != 0) {
-            cudaStreamSynchronize(ctx->stream);
-            if (rc == NZCB_E_CUDA || rc == NZCB_E_NOMEM) return rc;  // the device is gone: stop
-            if (!first_err) first_err = rc;
-            memset(out + i, 0, sizeof(nzcb_proof));
-        }
-    }
-    cudaEventRecord(ctx->ev1, ctx->stream);
-    NZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1);
-    return status ? 0 : first_err;
-}
-
+// ---- batches: independent proofs on `lanes` of the ctx, one host thread + stream each ------------------------
 // witness.cu
 namespace nzcb {
 int witness_dev(nzcb_ctx* ctx, const nzcb_circuit* c, const Fr* d_inputs, size_t B, Fr* d_wires, int32_t* d_status);
@@ -928,6 +907,107 @@ uint32_t circuit_n_total(const nzcb_circuit* c);
 uint32_t circuit_n_witness(const nzcb_circuit* c);
 uint32_t circuit_n_in(const nzcb_circuit* c);
 }  // namespace nzcb
+
+namespace {
+
+int lane_count(size_t B) {
+    int L = 3;
+    const char* env = getenv("NZCB_LANES");
+    if (env && atoi(env) >= 1 && atoi(env) <= 8) L = atoi(env);
+    if ((size_t)L > B) L = (int)B;
+    return L < 1 ? 1 : L;
+}
+
+// Runs item(lane_ctx, g) for g < B on lane_count(B) lanes.  item returns 0, a per-proof error (recorded by the
+// item itself) or a fatal one (NZCB_E_CUDA / NZCB_E_NOMEM), which stops the batch.  Device time of the whole batch
+// (root-stream events bracketing every lane) goes to ctx->last_ms.
+template <class Item, class Prologue>
+int run_on_lanes(nzcb_ctx* ctx, const nzcb_zkey* zk, size_t B, Item item, Prologue prologue) {
+    NZ_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int L = lane_count(B);
+    std::vector<nzcb_ctx*> lanes(L);
+    for (int l = 0; l < L; l++) {
+        lanes[l] = ctx_lane(ctx, l);
+        if (!lanes[l]) return ctx->fail(NZCB_E_CUDA, "cannot create lane %d", l);
+        lanes[l]->prof_on = ctx->prof_on;
+    }
+    {   // shared tables exist before any lane needs them
+        const Fr* w = nullptr;
+        NZ_TRY(get_twiddles_pub(ctx, zk->power, false, &w));
+        NZ_TRY(get_twiddles_pub(ctx, zk->power, true, &w));
+        NZ_TRY(get_twiddles_pub(ctx, zk->power + 2, false, &w));
+        NZ_TRY(get_twiddles_pub(ctx, zk->power + 2, true, &w));
+    }
+    NZ_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    for (int l = 0; l < L; l++) NZ_CUDA(ctx, cudaStreamWaitEvent(lanes[l]->stream, ctx->ev0, 0));
+    NZ_TRY(prologue(L));  // root-stream work the lanes consume (they wait on its events themselves)
+    std::atomic<size_t> next{0};
+    std::atomic<int> fatal{0};
+    auto worker = [&](int l) {
+        nzcb_ctx* lc = lanes[l];
+        cudaSetDevice(ctx->device);
+        for (;;) {
+            const size_t g = next.fetch_add(1);
+            if (g >= B || fatal.load()) break;
+            const int rc = item(lc, g);
+            if (rc == NZCB_E_CUDA || rc == NZCB_E_NOMEM) {
+                int expected = 0;
+                if (fatal.compare_exchange_strong(expected, rc)) {
+                    std::lock_guard<std::mutex> gl(ctx->mu);
+                    memcpy(ctx->err, lc->err, sizeof(ctx->err));
+                }
+                break;
+            }
+            if (rc != 0) {
+                std::lock_guard<std::mutex> gl(ctx->mu);
+                memcpy(ctx->err, lc->err, sizeof(ctx->err));
+            }
+        }
+    };
+    if (L == 1) {
+        worker(0);
+    } else {
+        std::vector<std::thread> th;
+        for (int l = 0; l < L; l++) th.emplace_back(worker, l);
+        for (auto& t : th) t.join();
+    }
+    for (int l = 0; l < L; l++) {
+        cudaEventRecord(lanes[l]->ev1, lanes[l]->stream);
+        cudaStreamWaitEvent(ctx->stream, lanes[l]->ev1, 0);
+    }
+    cudaEventRecord(ctx->ev1, ctx->stream);
+    const cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    for (int l = 0; l < L; l++) cudaStreamSynchronize(lanes[l]->stream);
+    if (fatal.load()) return fatal.load();
+    if (e != cudaSuccess) return ctx->fail(NZCB_E_CUDA, "CUDA error %s after a batch", cudaGetErrorString(e));
+    cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1);
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int32_t nzcb_plonk_prove_batch(nzcb_ctx* ctx, const nzcb_zkey* zk, const uint8_t* const* wtns,
+                                          const size_t* wtns_len, const uint8_t* blinders_le, size_t B, nzcb_proof* out,
+                                          uint8_t* public_le, int32_t* status) {
+    if (!ctx || !zk || !wtns || !wtns_len || !out) return NZCB_E_INVALID;
+    if (zk->ctx != ctx) return ctx->fail(NZCB_E_INVALID, "zkey was loaded on a different context");
+    if (B == 0) return 0;
+    std::atomic<int> first_err{0};
+    const int rc = run_on_lanes(ctx, zk, B, [&](nzcb_ctx* lc, size_t i) {
+        const int r = prove_one(lc, zk, wtns[i], wtns_len[i], blinders_le ? blinders_le + i * 9 * 32 : nullptr, out + i,
+                                public_le ? public_le + i * (size_t)zk->n_public * 32 : nullptr);
+        if (status) status[i] = r;
+        if (r != 0) {
+            cudaStreamSynchronize(lc->stream);
+            int expected = 0;
+            first_err.compare_exchange_strong(expected, r);
+            memset(out + i, 0, sizeof(nzcb_proof));
+        }
+        return r;
+    }, [](int) { return 0; });
+    if (rc != 0) return rc;
+    return status ? 0 : first_err.load();
+}
 
 // snarkjs plonk.fullProve: witness program on the GPU, the wires never leave HBM, then the prover
 static int32_t fullprove_impl(nzcb_ctx* ctx, const nzcb_circuit* cir, const nzcb_zkey* zk, const uint8_t* inputs_le,
@@ -954,52 +1034,77 @@ static int32_t fullprove_impl(nzcb_ctx* ctx, const nzcb_circuit* cir, const nzcb
     if (circuit_n_witness(cir) != n_w)
         return ctx->fail(NZCB_E_WITNESS, "Invalid witness length. Circuit: %u, witness: %u, %u", zk->n_vars,
                          circuit_n_witness(cir), zk->n_add);
-    NZ_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (B == 0) return 0;
     const size_t n_total = circuit_n_total(cir), n_in = circuit_n_in(cir), n_pub = zk->n_public;
     const size_t per_pass = n_total * sizeof(Fr);
-    size_t chunk = std::max<size_t>(1, ((size_t)4 << 30) / per_pass);
-    if (chunk > B) chunk = B;
-    Fr* d_w = (Fr*)ctx->scratch_get("fp_wires", chunk * per_pass);
-    Fr* d_in = (Fr*)ctx->scratch_get("fp_inputs", std::max<size_t>(32, chunk * n_in * sizeof(Fr)));
-    int32_t* d_st = (int32_t*)ctx->scratch_get("fp_status", chunk * sizeof(int32_t));
-    if (!d_w || !d_in || !d_st) return ctx->fail(NZCB_E_NOMEM, "fullProve: cannot allocate the witness buffers");
-    std::vector<uint8_t> pub(std::max<size_t>(1, n_pub) * 32);
-    cudaEventRecord(ctx->ev0, ctx->stream);
-    for (size_t done = 0; done < B; done += chunk) {
-        const size_t nb = std::min(chunk, B - done);
-        const Fr* cur_in = d_in;
-        if (inputs_on_device) cur_in = (const Fr*)inputs_le + done * n_in;
-        else if (n_in)
-            NZ_CUDA(ctx, cudaMemcpyAsync(d_in, inputs_le + done * n_in * 32, nb * n_in * 32, cudaMemcpyHostToDevice,
-                                         ctx->stream));
-        NZ_TRY(witness_dev(ctx, cir, cur_in, nb, d_w, d_st));
-        NZ_CUDA(ctx, cudaMemcpyAsync(status + done, d_st, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-        NZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        for (size_t i = 0; i < nb; i++) {
-            const size_t g = done + i;
-            if (status[g] != 0) {  // "Assert Failed": this pass is rejected, the batch goes on
-                memset(out + g, 0, sizeof(nzcb_proof));
-                continue;
+    // The witness program of the whole batch runs on the root stream in two launches: the first `lanes` passes, then
+    // the rest -- so the lanes start proving after one witness latency and the second launch hides behind them.
+    size_t cap = std::max<size_t>(1, ((size_t)16 << 30) / per_pass);
+    int32_t rc_all = 0;
+    float total_ms = 0.f;
+    for (size_t done = 0; done < B && rc_all == 0; done += cap) {
+        const size_t nb = std::min(cap, B - done);
+        Fr* d_w = (Fr*)ctx->scratch_get("fp_wires", nb * per_pass);
+        Fr* d_in = (Fr*)ctx->scratch_get("fp_inputs", std::max<size_t>(32, nb * n_in * sizeof(Fr)));
+        int32_t* d_st = (int32_t*)ctx->scratch_get("fp_status", std::max<size_t>(256, nb * sizeof(int32_t)));
+        if (!d_w || !d_in || !d_st) return ctx->fail(NZCB_E_NOMEM, "fullProve: cannot allocate the witness buffers");
+        cudaEvent_t ev_first = nullptr, ev_rest = nullptr;
+        if (cudaEventCreateWithFlags(&ev_first, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ev_rest, cudaEventDisableTiming) != cudaSuccess)
+            return ctx->fail(NZCB_E_CUDA, "fullProve: cannot create events");
+        size_t n_first = 0;
+        const uint8_t* in_chunk = inputs_le + done * n_in * 32;
+        const uint8_t* bl_chunk = blinders_le ? blinders_le + done * 9 * 32 : nullptr;
+        nzcb_proof* out_chunk = out + done;
+        uint8_t* pub_chunk = public_le ? public_le + done * n_pub * 32 : nullptr;
+        int32_t* st_chunk = status + done;
+        rc_all = run_on_lanes(ctx, zk, nb, [&](nzcb_ctx* lc, size_t g) -> int {
+            NZ_CUDA(lc, cudaStreamWaitEvent(lc->stream, g < n_first ? ev_first : ev_rest, 0));
+            const Fr* w = d_w + g * n_total;
+            uint8_t pub[32 * 64];
+            std::vector<uint8_t> pub_big;
+            uint8_t* pp = pub;
+            if (n_pub > 64) {
+                pub_big.resize(n_pub * 32);
+                pp = pub_big.data();
             }
-            const Fr* w = d_w + i * n_total;
-            if (n_pub) {
-                NZ_CUDA(ctx, cudaMemcpyAsync(pub.data(), w + 1, n_pub * 32, cudaMemcpyDeviceToHost, ctx->stream));
-                NZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            int32_t st = 0;
+            NZ_CUDA(lc, cudaMemcpyAsync(&st, d_st + g, sizeof(int32_t), cudaMemcpyDeviceToHost, lc->stream));
+            if (n_pub) NZ_CUDA(lc, cudaMemcpyAsync(pp, w + 1, n_pub * 32, cudaMemcpyDeviceToHost, lc->stream));
+            NZ_CUDA(lc, cudaStreamSynchronize(lc->stream));
+            st_chunk[g] = st;
+            if (st != 0) {  // "Assert Failed": this pass is rejected, the batch goes on
+                memset(out_chunk + g, 0, sizeof(nzcb_proof));
+                lc->fail(st, "Assert Failed");
+                return 0;
             }
-            const int rc = prove_core(ctx, zk, w, pub.data(), blinders_le ? blinders_le + g * 9 * 32 : nullptr, out + g,
-                                      public_le ? public_le + g * n_pub * 32 : nullptr);
-            status[g] = rc;
+            const int rc = prove_core(lc, zk, w, pp, bl_chunk ? bl_chunk + g * 9 * 32 : nullptr, out_chunk + g,
+                                      pub_chunk ? pub_chunk + g * n_pub * 32 : nullptr);
+            st_chunk[g] = rc;
             if (rc != 0) {
-                cudaStreamSynchronize(ctx->stream);
-                if (rc == NZCB_E_CUDA || rc == NZCB_E_NOMEM) return rc;
-                memset(out + g, 0, sizeof(nzcb_proof));
+                cudaStreamSynchronize(lc->stream);
+                memset(out_chunk + g, 0, sizeof(nzcb_proof));
             }
-        }
+            return rc;
+        }, [&](int lanes) -> int {
+            const Fr* cur_in = d_in;
+            if (inputs_on_device) cur_in = (const Fr*)in_chunk;
+            else if (n_in)
+                NZ_CUDA(ctx, cudaMemcpyAsync(d_in, in_chunk, nb * n_in * 32, cudaMemcpyHostToDevice, ctx->stream));
+            n_first = std::min<size_t>(nb, (size_t)lanes);
+            NZ_TRY(witness_dev(ctx, cir, cur_in, n_first, d_w, d_st));
+            NZ_CUDA(ctx, cudaEventRecord(ev_first, ctx->stream));
+            if (nb > n_first)
+                NZ_TRY(witness_dev(ctx, cir, cur_in + n_first * n_in, nb - n_first, d_w + n_first * n_total, d_st + n_first));
+            NZ_CUDA(ctx, cudaEventRecord(ev_rest, ctx->stream));
+            return 0;
+        });
+        cudaEventDestroy(ev_first);
+        cudaEventDestroy(ev_rest);
+        total_ms += ctx->last_ms;
     }
-    cudaEventRecord(ctx->ev1, ctx->stream);
-    NZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1);
-    return 0;
+    ctx->last_ms = total_ms;
+    return rc_all;
 }
 
 // ------------------------------------------------------------------ proof.json
