@@ -106,6 +106,7 @@ static inline unsigned div_up(size_t a, size_t b) { return (unsigned)((a + b - 1
 nzcb_ctx* ctx_lane(nzcb_ctx* root, int i);
 // ntt.cu
 int ntt_dev(nzcb_ctx* ctx, Fr* d_data, uint32_t log_n, bool inverse);
+int ntt_dev_tab(nzcb_ctx* ctx, Fr* d_data, uint32_t log_n, bool inverse, const Fr* d_out_factors);
 // msm.cu : result left in d_out (one G1XYZZ) ; scalars 8 x u32 each.  One-shot bases (window mode).
 int msm_dev(nzcb_ctx* ctx, const G1Affine* d_bases, const uint32_t* d_scalars, size_t n, bool scalars_mont,
             G1XYZZ* d_out);

@@ -75,6 +75,20 @@ __global__ void k_bitrev(Fr* __restrict__ a, uint32_t log_n, Fr scale, int do_sc
     }
 }
 
+// the same permutation with a per-element factor: a'[i] = a[rev(i)] * tab[i]   (coset iNTT: tab[i] = g^-i / N)
+__global__ void k_bitrev_tab(Fr* __restrict__ a, uint32_t log_n, const Fr* __restrict__ tab) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ((size_t)1 << log_n)) return;
+    const size_t r = log_n ? (size_t)(__brev((uint32_t)i) >> (32 - log_n)) : 0;
+    if (i < r) {
+        const Fr u = a[i], v = a[r];
+        a[i] = v * tab[i];
+        a[r] = u * tab[r];
+    } else if (i == r) {
+        a[i] = a[i] * tab[i];
+    }
+}
+
 // 2^log_n-th primitive root w[log_n]: w[28] = 5^((r-1)/2^28), w[i] = w[i+1]^2
 Fr fr_root_host(uint32_t log_n) {
     // (r - 1) >> 28
@@ -114,7 +128,10 @@ int get_twiddles_pub(nzcb_ctx* ctx, uint32_t log_n, bool inverse, const Fr** out
     return 0;
 }
 
-int ntt_dev(nzcb_ctx* ctx, Fr* d, uint32_t log_n, bool inverse) {
+int ntt_dev(nzcb_ctx* ctx, Fr* d, uint32_t log_n, bool inverse) { return ntt_dev_tab(ctx, d, log_n, inverse, nullptr); }
+
+// tab != nullptr: the final pass multiplies output element i by tab[i] INSTEAD of the uniform 1/N of the inverse
+int ntt_dev_tab(nzcb_ctx* ctx, Fr* d, uint32_t log_n, bool inverse, const Fr* tab) {
     if (log_n > 28) return ctx->fail(NZCB_E_INVALID, "ntt: log_n %u exceeds the 2-adicity of Fr (28)", log_n);
     if (log_n == 0) return 0;
     const Fr* W = nullptr;
@@ -133,7 +150,8 @@ int ntt_dev(nzcb_ctx* ctx, Fr* d, uint32_t log_n, bool inverse) {
     }
     Fr scale = Fr::one();
     if (inverse) scale = Fr::from_u64((uint64_t)1 << log_n).inv();
-    NZ_LAUNCH(ctx, k_bitrev, div_up((size_t)1 << log_n, 256), 256, 0, d, log_n, scale, inverse ? 1 : 0);
+    if (tab) NZ_LAUNCH(ctx, k_bitrev_tab, div_up((size_t)1 << log_n, 256), 256, 0, d, log_n, tab);
+    else NZ_LAUNCH(ctx, k_bitrev, div_up((size_t)1 << log_n, 256), 256, 0, d, log_n, scale, inverse ? 1 : 0);
     return 0;
 }
 

@@ -30,6 +30,14 @@ struct nzcb_zkey {
     Fr* d_sigma = nullptr;                                       // 3 x (n + 4n)
     Fr* d_lag = nullptr;                                         // max(nPublic,1) x (n + 4n)
     G1Table tab;                                                 // [tau^i]G1, i < n + 6, with window shifts (msm.cu)
+    // round 3 runs on the coset g * H_4n (Z_H never vanishes there): selectors, sigmas and the public-input
+    // Lagrange polynomials evaluated on it once per key
+    Fr g;                                                        // coset shift
+    Fr zh_inv[4];                                                // 1 / (g^n w4^p - 1)
+    Fr* d_cos[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // qm ql qr qo qc s1 s2 s3
+    Fr* d_cos_lag = nullptr;                                     // max(nPublic,1) x 4n
+    Fr* d_gpow = nullptr;                                        // g^k, k < n + 8
+    Fr* d_ginv = nullptr;                                        // g^-k / 4n, k < 4n
 };
 
 namespace {
@@ -130,13 +138,6 @@ __global__ void k_gather(const uint32_t* __restrict__ map, const Fr* __restrict_
     out[i] = v;
 }
 
-// dst[0..n) = src, dst[n..total) = 0
-__global__ void k_copy_pad(const Fr* __restrict__ src, size_t n, Fr* __restrict__ dst, size_t total) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    dst[i] = i < n ? src[i] : Fr::zero();
-}
-
 // pol (n + k coefficients) = coef + (pz[0] + pz[1] X + ...) * (X^n - 1)      (to4T, A.2 round 1)
 struct Blind {
     Fr pz[3];
@@ -177,100 +178,70 @@ __global__ void k_mul_inplace(Fr* __restrict__ a, const Fr* __restrict__ b, size
     a[i] = a[i] * b[i];
 }
 
-struct R3Args {
-    const Fr *A4, *B4, *C4, *Z4, *QM4, *QL4, *QR4, *QO4, *QC4, *S14, *S24, *S34, *L4, *pub, *W4n;
-    Fr b[10];
-    Fr beta, gamma, alpha, alpha2, k1, k2, wn;
-    Fr Z1[4], Z2[4], Z3[4];
-    uint32_t n, power, n_pub;
-    Fr *T, *Tz;
-};
-
-struct Pair {
-    Fr r, rz;
-};
-// (a + Zh ap)(b + Zh bp)(c + Zh cp)(d + Zh dp) split into the Zh-free part r and the cofactor of Zh, rz
-__device__ __forceinline__ Pair mul4(const Fr& a, const Fr& b, const Fr& c, const Fr& d, const Fr& ap, const Fr& bp,
-                                     const Fr& cp, const Fr& dp, const Fr& ap_bp, const Fr& z1, const Fr& z2,
-                                     const Fr& z3, bool on_domain) {
-    const Fr a_b = a * b, c_d = c * d;
-    const Fr ab1 = a * bp + ap * b;   // a_bp + ap_b
-    const Fr cd1 = c * dp + cp * d;   // c_dp + cp_d
-    const Fr cp_dp = cp * dp;
-    Pair o;
-    o.r = a_b * c_d;
-    const Fr a0 = ab1 * c_d + a_b * cd1;
-    if (on_domain) {  // Zh = 0 on every 4th point
-        o.rz = a0;
-        return o;
-    }
-    const Fr a1 = ap_bp * c_d + ab1 * cd1 + a_b * cp_dp;
-    const Fr a2 = ab1 * cp_dp + ap_bp * cd1;
-    const Fr a3 = ap_bp * cp_dp;
-    o.rz = a0 + z1 * a1 + z2 * a2 + z3 * a3;
-    return o;
+// out[k] = scale * g^k
+__global__ void k_pow_table(Fr* __restrict__ out, Fr g, Fr scale, size_t n) {
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    out[k] = g.pow_u64(k) * scale;
+}
+// coefficients of p(gX), zero-padded: out[k] = in[k] * g^k (k < m), 0 (m <= k < total)
+__global__ void k_scale_pad(const Fr* __restrict__ in, size_t m, const Fr* __restrict__ gpow, Fr* __restrict__ out,
+                            size_t total) {
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= total) return;
+    out[k] = k < m ? in[k] * gpow[k] : Fr::zero();
 }
 
-__global__ void __launch_bounds__(128) k_round3(R3Args g) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t n4 = (size_t)4 * g.n;
-    if (i >= n4) return;
-    const uint32_t p = (uint32_t)(i & 3);
-    const Fr x = domain_pow(g.W4n, g.power + 2, i);
-    const Fr a = g.A4[i], b = g.B4[i], c = g.C4[i], z = g.Z4[i];
-    const Fr zw = g.Z4[(i + 4) & (n4 - 1)];
-    const Fr ap = g.b[2] + g.b[1] * x;
-    const Fr bp = g.b[4] + g.b[3] * x;
-    const Fr cp = g.b[6] + g.b[5] * x;
-    const Fr zp = (g.b[7] * x + g.b[8]) * x + g.b[9];
-    const Fr xw = x * g.wn;
-    const Fr zwp = (g.b[7] * xw + g.b[8]) * xw + g.b[9];
-    const Fr l1 = g.L4[(size_t)g.n + i];
-
-    Fr pl = Fr::zero();
-    for (uint32_t j = 0; j < g.n_pub; j++) pl = pl - g.L4[(size_t)j * 5 * g.n + g.n + i] * g.pub[j];
-
-    const Fr z1 = g.Z1[p], z2 = g.Z2[p], z3 = g.Z3[p];
-    const Fr ap_bp = ap * bp;
-    // gate part
-    const Fr qm = g.QM4[i], ql = g.QL4[i], qr = g.QR4[i], qo = g.QO4[i], qc = g.QC4[i];
-    Fr e1 = (a * b) * qm + a * ql + b * qr + c * qo + pl + qc;
-    Fr e1z = (a * bp + ap * b + z1 * ap_bp) * qm + ap * ql + bp * qr + cp * qo;
-    // permutation parts
-    const Fr bx = g.beta * x;
-    const Pair e2 = mul4(a + bx + g.gamma, b + bx * g.k1 + g.gamma, c + bx * g.k2 + g.gamma, z, ap, bp, cp, zp, ap_bp,
-                         z1, z2, z3, p == 0);
-    const Pair e3 = mul4(a + g.beta * g.S14[i] + g.gamma, b + g.beta * g.S24[i] + g.gamma,
-                         c + g.beta * g.S34[i] + g.gamma, zw, ap, bp, cp, zwp, ap_bp, z1, z2, z3, p == 0);
-    const Fr e4 = (z - Fr::one()) * l1 * g.alpha2;
-    const Fr e4z = zp * l1 * g.alpha2;
-    g.T[i] = e1 + (e2.r - e3.r) * g.alpha + e4;
-    g.Tz[i] = e1z + (e2.rz - e3.rz) * g.alpha + e4z;
-}
-
-// t /= Z_H in coefficient space (A.2 round 3); flags[0] set if a coefficient above 3n-4 is non-zero
-__global__ void k_div_zh(Fr* __restrict__ t, uint32_t n, int* __restrict__ flags) {
+// "T Polynomial is not divisible" <=> the gate equation fails on some row of H (the permutation and L_1 parts
+// vanish on H by construction of Z, checked in round 2).  flags[0].
+struct RowArgs {
+    const Fr *A, *B, *C, *QM4, *QL4, *QR4, *QO4, *QC4, *pub;
+    uint32_t n, n_pub;
+    int* flags;
+};
+__global__ void __launch_bounds__(256) k_rowcheck(RowArgs q) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    Fr prev = t[i].neg();
-    t[i] = prev;
-    for (uint32_t k = 1; k < 4; k++) {
-        const size_t idx = (size_t)k * n + i;
-        prev = prev - t[idx];
-        t[idx] = prev;
-        if (idx > (size_t)3 * n - 4 && !prev.is_zero()) atomicOr(&flags[0], 1);
-    }
+    if (i >= q.n) return;
+    const size_t j = (size_t)4 * i;
+    const Fr a = q.A[i], b = q.B[i], c = q.C[i];
+    Fr v = (a * b) * q.QM4[j] + a * q.QL4[j] + b * q.QR4[j] + c * q.QO4[j] + q.QC4[j];
+    if (i < q.n_pub) v = v - q.pub[i];
+    if (!v.is_zero()) atomicOr(&q.flags[0], 1);
 }
-// t += tz (i <= 3n+5), tz must vanish above; flags[1]
-__global__ void k_add_tz(Fr* __restrict__ t, const Fr* __restrict__ tz, uint32_t n, int* __restrict__ flags) {
+
+// Quotient on the coset: t(x) = N'(x) / Z_H(x), x = g w_4n^i, with N' the full numerator of the blinded
+// polynomials (A.2 round 3: T + Z_H Tz = N' as polynomials, so t is the same polynomial snarkjs obtains from
+// its two half-computations).
+struct R3Args {
+    const Fr *A, *B, *C, *Z;  // blinded a, b, c, z on the coset (4n values each)
+    const Fr *QM, *QL, *QR, *QO, *QC, *S1, *S2, *S3, *LAG, *pub, *W4n;
+    Fr g, beta, gamma, alpha, alpha2, k1, k2;
+    Fr zh_inv[4];
+    uint32_t n, power, n_pub;
+    Fr* T;
+};
+__global__ void __launch_bounds__(128) k_round3(R3Args q) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t n4 = (size_t)4 * q.n;
+    if (i >= n4) return;
+    const Fr x = domain_pow(q.W4n, q.power + 2, i) * q.g;
+    const Fr a = q.A[i], b = q.B[i], c = q.C[i], z = q.Z[i];
+    const Fr zw = q.Z[(i + 4) & (n4 - 1)];
+    Fr pl = Fr::zero();
+    for (uint32_t j = 0; j < q.n_pub; j++) pl = pl - q.LAG[(size_t)j * n4 + i] * q.pub[j];
+    const Fr gate = (a * b) * q.QM[i] + a * q.QL[i] + b * q.QR[i] + c * q.QO[i] + q.QC[i] + pl;
+    const Fr bx = q.beta * x;
+    const Fr p1 = ((a + bx + q.gamma) * (b + bx * q.k1 + q.gamma)) * ((c + bx * q.k2 + q.gamma) * z);
+    const Fr p2 = ((a + q.beta * q.S1[i] + q.gamma) * (b + q.beta * q.S2[i] + q.gamma)) *
+                  ((c + q.beta * q.S3[i] + q.gamma) * zw);
+    const Fr l1 = (z - Fr::one()) * q.LAG[i] * q.alpha2;
+    q.T[i] = (gate + (p1 - p2) * q.alpha + l1) * q.zh_inv[i & 3];
+}
+// coefficients above 3n + 5 must vanish; flags[1]
+__global__ void k_check_high(const Fr* __restrict__ t, uint32_t n, int* __restrict__ flags) {
+    const size_t i = (size_t)3 * n + 6 + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)4 * n) return;
-    const Fr v = tz[i];
-    if (i > (size_t)3 * n + 5) {
-        if (!v.is_zero()) atomicOr(&flags[1], 1);
-    } else {
-        t[i] = t[i] + v;
-    }
+    if (!t[i].is_zero()) atomicOr(&flags[1], 1);
 }
 
 struct R4Args {
@@ -339,6 +310,10 @@ extern "C" void nzcb_zkey_free(nzcb_zkey* zk) {
     cudaFree(zk->d_sigma);
     cudaFree(zk->d_lag);
     g1_table_free(&zk->tab);
+    for (int i = 0; i < 8; i++) cudaFree(zk->d_cos[i]);
+    cudaFree(zk->d_cos_lag);
+    cudaFree(zk->d_gpow);
+    cudaFree(zk->d_ginv);
     delete zk;
 }
 
@@ -436,6 +411,52 @@ extern "C" int32_t nzcb_zkey_load(nzcb_ctx* ctx, const uint8_t* data, size_t len
         }
     }
 
+    {   // coset evaluations for round 3
+        zk->g = Fr::from_u64(7);
+        Fr gn = zk->g;
+        for (uint32_t i = 0; i < zk->power; i++) gn = gn.sqr();
+        const Fr w4 = fr_root_host(2);
+        Fr wp = Fr::one();
+        bool bad = false;
+        for (int pp = 0; pp < 4; pp++) {
+            const Fr d = gn * wp - Fr::one();
+            bad = bad || d.is_zero();
+            zk->zh_inv[pp] = d.inv();
+            wp = wp * w4;
+        }
+        if (bad) {
+            nzcb_zkey_free(zk);
+            return ctx->fail(NZCB_E_INVALID, "zkey: the coset shift lies in the 4n domain");
+        }
+        const size_t n4 = 4 * n;
+        ZK_CUDA(cudaMalloc(&zk->d_gpow, (n + 8) * sizeof(Fr)));
+        ZK_CUDA(cudaMalloc(&zk->d_ginv, n4 * sizeof(Fr)));
+        k_pow_table<<<div_up(n + 8, 256), 256, 0, ctx->stream>>>(zk->d_gpow, zk->g, Fr::one(), n + 8);
+        k_pow_table<<<div_up(n4, 256), 256, 0, ctx->stream>>>(zk->d_ginv, zk->g.inv(), Fr::from_u64(n4).inv(), n4);
+        ctx->launches += 2;
+        auto to_coset = [&](const Fr* coef, Fr* out) -> int {
+            k_scale_pad<<<div_up(n4, 256), 256, 0, ctx->stream>>>(coef, n, zk->d_gpow, out, n4);
+            ctx->launches++;
+            return ntt_dev(ctx, out, zk->power + 2, false);
+        };
+        for (int k = 0; k < 8; k++) {
+            ZK_CUDA(cudaMalloc(&zk->d_cos[k], n4 * sizeof(Fr)));
+            const Fr* coef = k < 5 ? zk->d_q[k] : zk->d_sigma + (size_t)(k - 5) * 5 * n;
+            if (to_coset(coef, zk->d_cos[k]) != 0) {
+                nzcb_zkey_free(zk);
+                return NZCB_E_CUDA;
+            }
+        }
+        ZK_CUDA(cudaMalloc(&zk->d_cos_lag, (size_t)n_lag * n4 * sizeof(Fr)));
+        for (uint32_t j = 0; j < n_lag; j++) {
+            if (to_coset(zk->d_lag + (size_t)j * 5 * n, zk->d_cos_lag + (size_t)j * n4) != 0) {
+                nzcb_zkey_free(zk);
+                return NZCB_E_CUDA;
+            }
+        }
+        ZK_CUDA(cudaGetLastError());
+    }
+
     // additions: level-schedule.  level(i) = 1 + max(level of operands that are themselves additions)
     const uint32_t n_w = zk->n_vars - zk->n_add;
     const uint32_t na = zk->n_add;
@@ -496,7 +517,7 @@ extern "C" int32_t nzcb_zkey_load(nzcb_ctx* ctx, const uint8_t* data, size_t len
 namespace {
 
 struct Bufs {
-    Fr *W, *A, *B, *C, *pol_a, *pol_b, *pol_c, *pol_z, *A4, *B4, *C4, *Z4, *num, *den, *T, *Tz, *pol_r, *pol_wxi,
+    Fr *W, *A, *B, *C, *pol_a, *pol_b, *pol_c, *pol_z, *A4, *B4, *C4, *Z4, *num, *den, *T, *pol_r, *pol_wxi,
         *quot, *quot2, *vals, *pub;
     G1XYZZ* pts;
     int* flags;
@@ -525,7 +546,6 @@ int get_bufs(nzcb_ctx* ctx, const nzcb_zkey* zk, Bufs& b) {
     GETBUF(num, "pv_num", n);
     GETBUF(den, "pv_den", n);
     GETBUF(T, "pv_T", 4 * n);
-    GETBUF(Tz, "pv_Tz", 4 * n);
     GETBUF(pol_r, "pv_pol_r", n + 8);
     GETBUF(pol_wxi, "pv_pol_wxi", n + 8);
     GETBUF(quot, "pv_quot", n + 8);
@@ -569,17 +589,18 @@ struct Tracer {
     }
 };
 
-// evaluations -> (blinded coefficient polynomial, unblinded 4n evaluations)   [snarkjs to4T]
+// evaluations -> (blinded coefficient polynomial, its 4n evaluations on the coset)   [role of snarkjs to4T]
 int to4t(nzcb_ctx* ctx, const nzcb_zkey* zk, const Fr* d_evals, Fr* d_pol, Fr* d_ext, const Fr* pz, int k) {
     const size_t n = zk->n;
     NZ_CUDA(ctx, cudaMemcpyAsync(d_pol, d_evals, n * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->stream));
     NZ_TRY(ntt_dev(ctx, d_pol, zk->power, true));
-    NZ_LAUNCH(ctx, k_copy_pad, div_up(4 * n, 256), 256, 0, d_pol, n, d_ext, 4 * n);
-    NZ_TRY(ntt_dev(ctx, d_ext, zk->power + 2, false));
     Blind bl;
     bl.k = k;
     for (int i = 0; i < 3; i++) bl.pz[i] = i < k ? pz[i] : Fr::zero();
     NZ_LAUNCH(ctx, k_blind, 1, 32, 0, d_pol, n, bl);
+    // the blinded polynomial on the coset g * H_4n (round 3)
+    NZ_LAUNCH(ctx, k_scale_pad, div_up(4 * n, 256), 256, 0, d_pol, n + (size_t)k, zk->d_gpow, d_ext, 4 * n);
+    NZ_TRY(ntt_dev(ctx, d_ext, zk->power + 2, false));
     return 0;
 }
 
@@ -745,34 +766,32 @@ int prove_core(nzcb_ctx* ctx, const nzcb_zkey* zk, const Fr* d_w_le, const uint8
     const Fr alpha2 = alpha * alpha;
     NZ_CUDA(ctx, cudaMemcpyAsync(b.pub, pub_m.data(), (size_t)(n_pub + 1) * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
     {
+        RowArgs q;
+        q.A = b.A; q.B = b.B; q.C = b.C;
+        q.QM4 = zk->d_q[0] + N; q.QL4 = zk->d_q[1] + N; q.QR4 = zk->d_q[2] + N; q.QO4 = zk->d_q[3] + N; q.QC4 = zk->d_q[4] + N;
+        q.pub = b.pub; q.n = n; q.n_pub = n_pub; q.flags = b.flags;
+        NZ_LAUNCH(ctx, k_rowcheck, div_up(n, 256), 256, 0, q);
+    }
+    {
         R3Args g;
-        g.A4 = b.A4; g.B4 = b.B4; g.C4 = b.C4; g.Z4 = b.Z4;
-        g.QM4 = zk->d_q[0] + N; g.QL4 = zk->d_q[1] + N; g.QR4 = zk->d_q[2] + N; g.QO4 = zk->d_q[3] + N; g.QC4 = zk->d_q[4] + N;
-        g.S14 = S14; g.S24 = S24; g.S34 = S34; g.L4 = zk->d_lag; g.pub = b.pub; g.W4n = W4n;
-        for (int i = 0; i < 10; i++) g.b[i] = bl[i];
-        g.beta = beta; g.gamma = gamma; g.alpha = alpha; g.alpha2 = alpha2; g.k1 = zk->k1; g.k2 = zk->k2;
-        g.wn = fr_root_host(zk->power);
-        const Fr w4 = fr_root_host(2), one = Fr::one(), two = one + one, four = two + two, eight = four + four;
-        const Fr zero = Fr::zero();
-        g.Z1[0] = zero; g.Z1[1] = w4 - one; g.Z1[2] = zero - two; g.Z1[3] = zero - one - w4;
-        g.Z2[0] = zero; g.Z2[1] = zero - two * w4; g.Z2[2] = four; g.Z2[3] = two * w4;
-        g.Z3[0] = zero; g.Z3[1] = two + two * w4; g.Z3[2] = zero - eight; g.Z3[3] = two - two * w4;
-        g.n = n; g.power = zk->power; g.n_pub = n_pub; g.T = b.T; g.Tz = b.Tz;
+        g.A = b.A4; g.B = b.B4; g.C = b.C4; g.Z = b.Z4;
+        g.QM = zk->d_cos[0]; g.QL = zk->d_cos[1]; g.QR = zk->d_cos[2]; g.QO = zk->d_cos[3]; g.QC = zk->d_cos[4];
+        g.S1 = zk->d_cos[5]; g.S2 = zk->d_cos[6]; g.S3 = zk->d_cos[7]; g.LAG = zk->d_cos_lag; g.pub = b.pub; g.W4n = W4n;
+        g.g = zk->g; g.beta = beta; g.gamma = gamma; g.alpha = alpha; g.alpha2 = alpha2; g.k1 = zk->k1; g.k2 = zk->k2;
+        for (int i = 0; i < 4; i++) g.zh_inv[i] = zk->zh_inv[i];
+        g.n = n; g.power = zk->power; g.n_pub = n_pub; g.T = b.T;
         NZ_LAUNCH(ctx, k_round3, div_up(4 * N, 128), 128, 0, g);
     }
     tr_.mark("r3 quotient");
-    NZ_TRY(ntt_dev(ctx, b.T, zk->power + 2, true));
-    NZ_LAUNCH(ctx, k_div_zh, div_up(n, 256), 256, 0, b.T, n, b.flags);
-    NZ_TRY(ntt_dev(ctx, b.Tz, zk->power + 2, true));
-    NZ_LAUNCH(ctx, k_add_tz, div_up(4 * N, 256), 256, 0, b.T, b.Tz, n, b.flags);
+    NZ_TRY(ntt_dev_tab(ctx, b.T, zk->power + 2, true, zk->d_ginv));  // t(gX) -> t(X): factor g^-k / 4n per coefficient
+    NZ_LAUNCH(ctx, k_check_high, div_up(n, 256), 256, 0, b.T, n, b.flags);
     {
         int fl[4];
         NZ_CUDA(ctx, cudaMemcpyAsync(fl, b.flags, sizeof(fl), cudaMemcpyDeviceToHost, ctx->stream));
         NZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        if (fl[0]) return ctx->fail(NZCB_E_DIVIDE, "T Polynomial is not divisible");
-        if (fl[1]) return ctx->fail(NZCB_E_DIVIDE, "Tz Polynomial is not well calculated");
+        if (fl[0] || fl[1]) return ctx->fail(NZCB_E_DIVIDE, "T Polynomial is not divisible");
     }
-    tr_.mark("r3 intt x2");
+    tr_.mark("r3 intt");
     Fr* pol_t = b.T;  // 3n + 6 coefficients
     {
         const uint32_t* sc[3] = {(const uint32_t*)pol_t, (const uint32_t*)(pol_t + N), (const uint32_t*)(pol_t + 2 * N)};
