@@ -235,11 +235,16 @@ def main():
     barrier()
     e2e = world * steps * B / e2e_s
 
-    # ---- single-proof latency (B = 1), device-resident
+    # ---- single-proof latency (B = 1, one lane) with the dominant kernel timed alone on the GPU
     one = pr.marshal_passes(all_passes[0][:1])
+    check(pr.prove_raw(one, 1))
+    ctx.profile(True)
     t0 = time.perf_counter()
     check(pr.prove_raw(one, 1))
     latency_ms = 1000 * (time.perf_counter() - t0)
+    alone_dev_ms = ctx.last_device_ms
+    n_alone, alone_ms, alone_modmul = ctx.profile_read()
+    ctx.profile(False)
 
     if rank != 0:
         return 0
@@ -255,13 +260,20 @@ def main():
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "r01_msm_accum_ncu.json")) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
+            traffic = json.load(f).get("dram_bytes_per_launch")  # ncu --set full: dram__bytes_read.sum + write.sum
     except Exception:
         pass
+    alone = alone_modmul * 264.0 / (alone_ms / 1000.0) if alone_ms > 0 else 0.0
     roofline = {"bound": "imad", "kernel": "k_msm_accum (MSM bucket accumulation)", "achieved": achieved / 1e12,
                 "peak": imad_peak / 1e12, "unit": "TIMAD32/s", "frac": achieved / imad_peak if imad_peak else None,
                 "traffic": traffic, "launches": n_launch, "avg_launch_ms": acc_ms / n_launch if n_launch else None,
                 "kernel_share_of_step": acc_ms / (dev_ms) if dev_ms else None,
+                "note": "timed region: lanes share the GPU, so an accumulation launch can overlap other lanes' kernels; "
+                        "`alone` is the same kernel in a single-proof, single-lane run",
+                "alone": {"achieved": alone / 1e12, "frac": alone / imad_peak if imad_peak else None, "launches": n_alone,
+                          "avg_launch_ms": alone_ms / n_alone if n_alone else None,
+                          "kernel_share_of_proof": alone_ms / alone_dev_ms if alone_dev_ms else None},
+                "algorithmic_unit": "160 modmul per MSM point x 264 IMAD32 per modmul (SURVEY.md 8d)",
                 "peak_source": "measured live: nzcb_microbench kind 0 (IMAD), this GPU; MEASURED_PEAKS.json has no integer-pipe figure",
                 "hbm_gbs_measured_peak": hbm_peak}
 

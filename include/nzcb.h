@@ -105,6 +105,10 @@ int32_t nzcb_msm_g1_table(nzcb_ctx* ctx, const nzcb_g1_table* t, const uint8_t* 
 int32_t nzcb_msm_g1_table_dev(nzcb_ctx* ctx, const nzcb_g1_table* t, const void* const* d_scalars, const size_t* n,
                               int32_t K, uint8_t* out_affine_lem);
 
+/* Lagrange-basis SRS: [L_i(tau)]G1, i < 2^log_n, from the monomial points [tau^j]G1, j < 2^log_n -- the group
+ * inverse DFT of `snarkjs powersoftau prepare phase2` (ptau sections 12-15).  Both buffers n x 64 B affine LEM. */
+int32_t nzcb_g1_lagrange_basis(nzcb_ctx* ctx, const uint8_t* srs_affine_lem, uint32_t log_n, uint8_t* out_affine_lem);
+
 /* ---- SRS + setup: `snarkjs powersoftau new` / `plonk setup` roles --------- */
 /* [tau^i]G1, i < count, affine LEM (insecure known-trapdoor SRS, Makefile:64-67 role) */
 int32_t nzcb_srs_g1(nzcb_ctx* ctx, const uint8_t tau_le[32], size_t count, uint8_t* out_affine_lem);

@@ -74,6 +74,7 @@ SIGNATURES = {
     "nzcb_g1_table_free": (None, [_vp]),
     "nzcb_msm_g1_table": (_i32, [_vp, _vp, _vp, _sz, _vp]),
     "nzcb_msm_g1_table_dev": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp]),
+    "nzcb_g1_lagrange_basis": (_i32, [_vp, _vp, _u32, _vp]),
     "nzcb_profile": (_i32, [_vp, _i32]),
     "nzcb_profile_read": (_i32, [_vp, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_double),
                                  ctypes.POINTER(ctypes.c_double)]),

@@ -292,8 +292,30 @@ struct alignas(32) Fp {
         nz_merge(r.v, X, Y);
         return reduce_once(r);
     }
+    // the same product with the eight rows rolled into a 4-trip loop (two rows per trip, the multiplier limbs
+    // rotated through registers): ~1/3 of the code of mul_ptx, for instruction-cache-bound callers
+    static NZ_D Fp mul_rolled(const Fp& a, const Fp& b) {
+        uint32_t X[8], Y[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) X[j] = Y[j] = 0;
+        uint32_t b0 = b.v[0], b1 = b.v[1], b2 = b.v[2], b3 = b.v[3], b4 = b.v[4], b5 = b.v[5], b6 = b.v[6], b7 = b.v[7];
+#pragma unroll 1
+        for (int it = 0; it < 4; it++) {
+            // (E = X, O = Y) holds the running value; Y[0] is dead on entry
+            nz_mad_row(X, Y, a.v, b0);   // note: row adds a*bi to E/O given E at 0..7, O[1..7] at 0..6
+            nz_redc_row<P>(X, Y);
+            nz_mad_row(Y, X, a.v, b1);
+            nz_redc_row<P>(Y, X);
+            const uint32_t t0 = b0, t1 = b1;
+            b0 = b2; b1 = b3; b2 = b4; b3 = b5; b4 = b6; b5 = b7; b6 = t0; b7 = t1;
+        }
+        Fp r;
+        nz_merge(r.v, X, Y);
+        return reduce_once(r);
+    }
     friend NZ_HD Fp operator*(const Fp& a, const Fp& b) { return mul_ptx(a, b); }
 #else
+    static NZ_HD Fp mul_rolled(const Fp& a, const Fp& b) { return mul_portable(a, b); }
     friend NZ_HD Fp operator*(const Fp& a, const Fp& b) { return mul_portable(a, b); }
 #endif
     NZ_HD Fp sqr() const { return *this * *this; }

@@ -85,6 +85,9 @@ struct MulInline {
     static __device__ __forceinline__ Fq mul(const Fq& a, const Fq& b) { return a * b; }
 };
 __device__ __noinline__ Fq fq_mul_call(Fq a, Fq b) { return a * b; }
+struct MulRolled {
+    static __device__ __forceinline__ Fq mul(const Fq& a, const Fq& b) { return Fq::mul_rolled(a, b); }
+};
 struct MulCall {
     static __device__ __forceinline__ Fq mul(const Fq& a, const Fq& b) { return fq_mul_call(a, b); }
 };
@@ -210,7 +213,7 @@ extern "C" int32_t nzcb_microbench(nzcb_ctx* ctx, int32_t kind, uint32_t iters, 
 // 128 thr x 3 CTA/SM (168 regs), 3 = inlined 256 thr x 2, 4 = call 256 x 3.  Result: mixed additions per second.
 extern "C" int32_t nzcb_microbench_madd(nzcb_ctx* ctx, int32_t variant, uint32_t iters, uint32_t log_table,
                                         double* madds_per_s) {
-    if (!ctx || !madds_per_s || variant < 0 || variant > 4 || log_table > 24) return NZCB_E_INVALID;
+    if (!ctx || !madds_per_s || variant < 0 || variant > 7 || log_table > 24) return NZCB_E_INVALID;
     const uint32_t n = 1u << log_table;
     G1Affine* tab = (G1Affine*)ctx->scratch_get("madd_tab", (size_t)n * sizeof(G1Affine));
     if (!tab) return ctx->fail(NZCB_E_NOMEM, "microbench: out of memory");
@@ -219,6 +222,8 @@ extern "C" int32_t nzcb_microbench_madd(nzcb_ctx* ctx, int32_t variant, uint32_t
     if (variant == 2) bps = 3;
     if (variant == 3) { threads = 256; bps = 2; }
     if (variant == 4) { threads = 256; bps = 3; }
+    if (variant == 6) bps = 5;
+    if (variant == 7) { threads = 256; bps = 2; }
     const uint32_t grid = (uint32_t)ctx->sm_count * bps;
     uint32_t* d = (uint32_t*)ctx->scratch_get("microbench", (size_t)grid * threads * 4);
     if (!d) return ctx->fail(NZCB_E_NOMEM, "microbench: out of memory");
@@ -229,7 +234,10 @@ extern "C" int32_t nzcb_microbench_madd(nzcb_ctx* ctx, int32_t variant, uint32_t
             case 1: NZ_LAUNCH(ctx, (k_madd_bench<MulCall, 128, 4>), grid, threads, 0, tab, n - 1, iters, d); break;
             case 2: NZ_LAUNCH(ctx, (k_madd_bench<MulInline, 128, 3>), grid, threads, 0, tab, n - 1, iters, d); break;
             case 3: NZ_LAUNCH(ctx, (k_madd_bench<MulInline, 256, 2>), grid, threads, 0, tab, n - 1, iters, d); break;
-            default: NZ_LAUNCH(ctx, (k_madd_bench<MulCall, 256, 3>), grid, threads, 0, tab, n - 1, iters, d); break;
+            case 4: NZ_LAUNCH(ctx, (k_madd_bench<MulCall, 256, 3>), grid, threads, 0, tab, n - 1, iters, d); break;
+            case 5: NZ_LAUNCH(ctx, (k_madd_bench<MulRolled, 128, 4>), grid, threads, 0, tab, n - 1, iters, d); break;
+            case 6: NZ_LAUNCH(ctx, (k_madd_bench<MulRolled, 128, 5>), grid, threads, 0, tab, n - 1, iters, d); break;
+            default: NZ_LAUNCH(ctx, (k_madd_bench<MulRolled, 256, 2>), grid, threads, 0, tab, n - 1, iters, d); break;
         }
         NZ_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
         NZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -30,6 +30,9 @@ struct nzcb_zkey {
     Fr* d_sigma = nullptr;                                       // 3 x (n + 4n)
     Fr* d_lag = nullptr;                                         // max(nPublic,1) x (n + 4n)
     G1Table tab;                                                 // [tau^i]G1, i < n + 6, with window shifts (msm.cu)
+    // round 1 commits in the Lagrange basis (g1fft.cu): [L_i(tau)]G1, i < n, then [1], [tau], [tau^n], [tau^(n+1)]
+    // for the blinding terms -- n + 4 bases, the scalars are the wire values themselves
+    G1Table tab_lag;
     // round 3 runs on the coset g * H_4n (Z_H never vanishes there): selectors, sigmas and the public-input
     // Lagrange polynomials evaluated on it once per key
     Fr g;                                                        // coset shift
@@ -172,6 +175,16 @@ __global__ void __launch_bounds__(128) k_round2_terms(R2Args a) {
     a.den[i] = d1 * (d2 * d3);
 }
 
+// the four blinding scalars of the Lagrange-basis commitment, after the n evaluations:
+// pol = a + (pz0 + pz1 X)(X^n - 1)  ->  [1]: -pz0, [tau]: -pz1, [tau^n]: pz0, [tau^(n+1)]: pz1
+__global__ void k_blind_scalars(Fr* __restrict__ evals, size_t n, Fr pz0, Fr pz1) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    evals[n] = pz0.neg();
+    evals[n + 1] = pz1.neg();
+    evals[n + 2] = pz0;
+    evals[n + 3] = pz1;
+}
+
 __global__ void k_mul_inplace(Fr* __restrict__ a, const Fr* __restrict__ b, size_t n) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -310,6 +323,7 @@ extern "C" void nzcb_zkey_free(nzcb_zkey* zk) {
     cudaFree(zk->d_sigma);
     cudaFree(zk->d_lag);
     g1_table_free(&zk->tab);
+    g1_table_free(&zk->tab_lag);
     for (int i = 0; i < 8; i++) cudaFree(zk->d_cos[i]);
     cudaFree(zk->d_cos_lag);
     cudaFree(zk->d_gpow);
@@ -404,7 +418,18 @@ extern "C" int32_t nzcb_zkey_load(nzcb_ctx* ctx, const uint8_t* data, size_t len
             return ctx->fail(NZCB_E_NOMEM, "zkey: cannot allocate the SRS staging buffer");
         }
         ZK_CUDA(cudaMemcpyAsync(d_ptau, sec[14].p, sec[14].size, cudaMemcpyHostToDevice, ctx->stream));
-        const int rc = g1_table_build(ctx, d_ptau, n + 6, &zk->tab);
+        int rc = g1_table_build(ctx, d_ptau, n + 6, &zk->tab);
+        G1Affine* d_lagpts = (G1Affine*)ctx->scratch_get("zk_lag_pts", (n + 4) * sizeof(G1Affine));
+        if (rc == 0 && !d_lagpts) rc = ctx->fail(NZCB_E_NOMEM, "zkey: cannot allocate the Lagrange-basis staging buffer");
+        if (rc == 0) rc = g1_lagrange_basis(ctx, d_ptau, zk->power, d_lagpts);
+        if (rc == 0) {
+            const size_t src[4] = {0, 1, (size_t)n, (size_t)n + 1};
+            for (int k = 0; k < 4 && rc == 0; k++)
+                if (cudaMemcpyAsync(d_lagpts + n + k, d_ptau + src[k], sizeof(G1Affine), cudaMemcpyDeviceToDevice,
+                                    ctx->stream) != cudaSuccess)
+                    rc = ctx->fail(NZCB_E_CUDA, "zkey: copy of the blinding bases failed");
+        }
+        if (rc == 0) rc = g1_table_build(ctx, d_lagpts, n + 4, &zk->tab_lag);
         if (rc != 0) {
             nzcb_zkey_free(zk);
             return rc;
@@ -532,9 +557,9 @@ struct Bufs {
 int get_bufs(nzcb_ctx* ctx, const nzcb_zkey* zk, Bufs& b) {
     const size_t n = zk->n;
     GETBUF(W, "pv_W", zk->n_vars + 1);
-    GETBUF(A, "pv_A", n);
-    GETBUF(B, "pv_B", n);
-    GETBUF(C, "pv_C", n);
+    GETBUF(A, "pv_A", n + 8);
+    GETBUF(B, "pv_B", n + 8);
+    GETBUF(C, "pv_C", n + 8);
     GETBUF(pol_a, "pv_pol_a", n + 8);
     GETBUF(pol_b, "pv_pol_b", n + 8);
     GETBUF(pol_c, "pv_pol_c", n + 8);
@@ -685,11 +710,14 @@ int prove_core(nzcb_ctx* ctx, const nzcb_zkey* zk, const Fr* d_w_le, const uint8
     }
     tr_.mark("r1 ntt");
     G1Affine cA, cB, cC, cZ, cT1, cT2, cT3, cWxi, cWxiw;
-    {
-        const uint32_t* sc[3] = {(const uint32_t*)b.pol_a, (const uint32_t*)b.pol_b, (const uint32_t*)b.pol_c};
-        const size_t sn[3] = {(size_t)n + 2, (size_t)n + 2, (size_t)n + 2};
+    {   // Lagrange basis: the scalars are the wire values (mostly 0 / +-1 / bytes) plus four blinding terms
+        NZ_LAUNCH(ctx, k_blind_scalars, 1, 32, 0, b.A, (size_t)n, bl[2], bl[1]);
+        NZ_LAUNCH(ctx, k_blind_scalars, 1, 32, 0, b.B, (size_t)n, bl[4], bl[3]);
+        NZ_LAUNCH(ctx, k_blind_scalars, 1, 32, 0, b.C, (size_t)n, bl[6], bl[5]);
+        const uint32_t* sc[3] = {(const uint32_t*)b.A, (const uint32_t*)b.B, (const uint32_t*)b.C};
+        const size_t sn[3] = {(size_t)n + 4, (size_t)n + 4, (size_t)n + 4};
         G1Affine r[3];
-        NZ_TRY(msm_table_dev(ctx, zk->tab, sc, sn, 3, true, b.pts));
+        NZ_TRY(msm_table_dev(ctx, zk->tab_lag, sc, sn, 3, true, b.pts));
         NZ_TRY(msm_to_host_affine(ctx, b.pts, r, 3));
         cA = r[0]; cB = r[1]; cC = r[2];
     }

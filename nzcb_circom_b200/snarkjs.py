@@ -289,6 +289,16 @@ class _Powersoftau:
         return bytes(out)
 
 
+    def lagrange_g1(self, srs_g1_lem, power, ctx=None):
+        """[L_i(tau)]G1 for the 2^power domain from the tauG1 points: the Lagrange section `snarkjs powersoftau
+        prepare phase2` appends to a .ptau (sections 12-15)."""
+        ctx = ctx or default_context()
+        n = 1 << power
+        out = (ctypes.c_uint8 * (64 * n))()
+        ctx.check(ctx.lib.nzcb_g1_lagrange_basis(ctx.h, as_cbuf(bytes(srs_g1_lem[:64 * n])), power, out))
+        return bytes(out)
+
+
 class _Wtns:
     def calculate(self, input, circuit, ctx=None):
         """snarkjs.wtns.calculate(input, wasmFile, {type:"mem"}) -> .wtns bytes.  `circuit` is a

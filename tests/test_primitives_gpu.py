@@ -183,3 +183,21 @@ def test_table_msm_srs_identity_large(ctx, log_n):
         assert b.g1_from_lem(got_t) == exp
         assert G1.multiExpAffine(srs, buf, ctx) == got_t
     tab.close()
+
+
+@pytest.mark.parametrize("log_n", [0, 1, 2, 5, 8])
+def test_lagrange_basis_matches_trapdoor(ctx, log_n):
+    """group inverse DFT of the SRS: out[i] == L_i(tau) * G with L_i(tau) = (1/n) sum_j w^(-ij) tau^j"""
+    from nzcb_circom_b200.snarkjs import powersoftau
+    from oracle.keccak import hash_to_fr
+
+    tau = hash_to_fr(b"nzcb-b200-tau")
+    n = 1 << log_n
+    srs = powersoftau.new_g1(tau, n, ctx)
+    got = powersoftau.lagrange_g1(srs, log_n, ctx)
+    w = b.fr_root(log_n) if log_n else 1
+    n_inv = pow(n, -1, b.R_MOD)
+    for i in sorted({0, 1 % n, n // 2, n - 1}):
+        wi = pow(w, -i, b.R_MOD)
+        li = sum(pow(wi, j, b.R_MOD) * pow(tau, j, b.R_MOD) for j in range(n)) * n_inv % b.R_MOD
+        assert b.g1_from_lem(got[64 * i:64 * i + 64]) == b.g1_mul(b.G1_GEN, li)
