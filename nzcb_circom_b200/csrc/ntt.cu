@@ -7,14 +7,20 @@
 // "row" are 32 consecutive 32-byte elements (1 KiB, fully coalesced) for all
 // but the last two passes, where every thread reads whole 32-byte sectors of
 // its own contiguous run.  Twiddles come from a per-size table w^t, t < N/2,
-// read with unit stride in the early stages (coalesced LDG.128 pairs) and
-// served from L1/L2 in the late ones.  A final pass undoes the bit reversal
-// (and folds in 1/N for the inverse).
+// read with unit stride in the early stages and served from L1/L2 in the late
+// ones.  The first launch writes a ping-pong buffer, the last one scatters to
+// bit-reversed (= natural) positions in the caller's array and applies 1/N or
+// the caller's per-element factors (coset transforms) -- no separate
+// permutation pass.
 //
 // Roofline: (N/2) log2 N modmul = 132 N log2 N IMAD32; HBM traffic
-// is 64 N bytes per pass, ceil(log2 N / 3) + 1 passes -- integer-pipe bound.
+// is 64 N bytes per launch, ceil(log2 N / 3) launches -- integer-pipe bound.
+// A shared-memory variant (6-8 stages per launch, warp-private transposes) was
+// measured slower at 2^23 (3.6 vs 2.9 ms: its 36 inlined multiplies thrash the
+// instruction cache, ncu stall_no_instruction 8.6) and was dropped.
 #include "common.cuh"
 #include "poly.cuh"
+#include <stdlib.h>
 
 namespace nzcb {
 
@@ -24,9 +30,13 @@ __global__ void k_twiddle_fill(Fr* __restrict__ W, Fr w, size_t half) {
     W[t] = w.pow_u64(t);
 }
 
-template <int R>
-__global__ void __launch_bounds__(256) k_ntt_pass(Fr* __restrict__ a, const Fr* __restrict__ W, uint32_t log_n,
-                                                   uint32_t s) {
+// One launch = R radix-2 stages [s, s+R) in registers.  `last`: the results go to their bit-reversed positions
+// (natural-order output) multiplied by tab[position] or by `scale` -- so a transform is ceil(log2 N / 3) launches,
+// first one out of place into a ping-pong buffer, last one back into the caller's array.
+template <int R, int TH, int MINB>
+__global__ void __launch_bounds__(TH, MINB) k_ntt_pass(const Fr* in, Fr* out, const Fr* __restrict__ W, uint32_t log_n,
+                                                       uint32_t s, int last, Fr scale, int do_scale,
+                                                       const Fr* __restrict__ tab) {
     constexpr int M = 1 << R;
     const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t log_q = log_n - s - R;
@@ -37,7 +47,7 @@ __global__ void __launch_bounds__(256) k_ntt_pass(Fr* __restrict__ a, const Fr* 
 
     Fr x[M];
 #pragma unroll
-    for (int m = 0; m < M; m++) x[m] = a[p + (size_t)m * q];
+    for (int m = 0; m < M; m++) x[m] = in[p + (size_t)m * q];
 
 #pragma unroll
     for (int t = 0; t < R; t++) {
@@ -53,39 +63,19 @@ __global__ void __launch_bounds__(256) k_ntt_pass(Fr* __restrict__ a, const Fr* 
             x[m + dm] = (u - v) * w;
         }
     }
+    if (!last) {
 #pragma unroll
-    for (int m = 0; m < M; m++) a[p + (size_t)m * q] = x[m];
-}
-
-// in-place bit-reversal permutation; scale != nullptr multiplies every element by *scale
-__global__ void k_bitrev(Fr* __restrict__ a, uint32_t log_n, Fr scale, int do_scale) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= ((size_t)1 << log_n)) return;
-    const size_t r = log_n ? (size_t)(__brev((uint32_t)i) >> (32 - log_n)) : 0;
-    if (i < r) {
-        Fr u = a[i], v = a[r];
-        if (do_scale) {
-            u = u * scale;
-            v = v * scale;
+        for (int m = 0; m < M; m++) out[p + (size_t)m * q] = x[m];
+    } else {
+#pragma unroll
+        for (int m = 0; m < M; m++) {
+            const size_t idx = p + (size_t)m * q;
+            const size_t r = (size_t)(__brev((uint32_t)idx) >> (32 - log_n));
+            Fr o = x[m];
+            if (tab) o = o * tab[r];
+            else if (do_scale) o = o * scale;
+            out[r] = o;
         }
-        a[i] = v;
-        a[r] = u;
-    } else if (i == r && do_scale) {
-        a[i] = a[i] * scale;
-    }
-}
-
-// the same permutation with a per-element factor: a'[i] = a[rev(i)] * tab[i]   (coset iNTT: tab[i] = g^-i / N)
-__global__ void k_bitrev_tab(Fr* __restrict__ a, uint32_t log_n, const Fr* __restrict__ tab) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= ((size_t)1 << log_n)) return;
-    const size_t r = log_n ? (size_t)(__brev((uint32_t)i) >> (32 - log_n)) : 0;
-    if (i < r) {
-        const Fr u = a[i], v = a[r];
-        a[i] = v * tab[i];
-        a[r] = u * tab[r];
-    } else if (i == r) {
-        a[i] = a[i] * tab[i];
     }
 }
 
@@ -136,22 +126,34 @@ int ntt_dev_tab(nzcb_ctx* ctx, Fr* d, uint32_t log_n, bool inverse, const Fr* ta
     if (log_n == 0) return 0;
     const Fr* W = nullptr;
     NZ_TRY(get_twiddles_pub(ctx, log_n, inverse, &W));
-    uint32_t s = 0;
-    const uint32_t rem = log_n % 3;
-    if (rem == 1) {
-        NZ_LAUNCH(ctx, k_ntt_pass<1>, div_up((size_t)1 << (log_n - 1), 256), 256, 0, d, W, log_n, s);
-        s += 1;
-    } else if (rem == 2) {
-        NZ_LAUNCH(ctx, k_ntt_pass<2>, div_up((size_t)1 << (log_n - 2), 256), 256, 0, d, W, log_n, s);
-        s += 2;
-    }
-    for (; s < log_n; s += 3) {
-        NZ_LAUNCH(ctx, k_ntt_pass<3>, div_up((size_t)1 << (log_n - 3), 256), 256, 0, d, W, log_n, s);
-    }
     Fr scale = Fr::one();
     if (inverse) scale = Fr::from_u64((uint64_t)1 << log_n).inv();
-    if (tab) NZ_LAUNCH(ctx, k_bitrev_tab, div_up((size_t)1 << log_n, 256), 256, 0, d, log_n, tab);
-    else NZ_LAUNCH(ctx, k_bitrev, div_up((size_t)1 << log_n, 256), 256, 0, d, log_n, scale, inverse ? 1 : 0);
+    Fr* tmp = (Fr*)ctx->scratch_get("ntt_tmp", ((size_t)1 << log_n) * sizeof(Fr));
+    if (!tmp) return ctx->fail(NZCB_E_NOMEM, "ntt: cannot allocate the ping-pong buffer");
+    static const int variant = [] {
+        const char* e = getenv("NZCB_NTT_VAR");
+        return e ? atoi(e) : 2;
+    }();
+    const uint32_t rem = log_n % 3;
+    const uint32_t n_pass = log_n / 3 + (rem ? 1 : 0);
+    uint32_t s = 0;
+    for (uint32_t pi = 0; pi < n_pass; pi++) {
+        const uint32_t R = (pi == 0 && rem) ? rem : 3;
+        const int last = pi + 1 == n_pass;
+        const Fr* src = pi == 0 ? d : tmp;
+        Fr* dst = (last && n_pass > 1) ? d : tmp;
+        const size_t n_thr = (size_t)1 << (log_n - R);
+        const int dsc = inverse ? 1 : 0;
+        if (R == 1) NZ_LAUNCH(ctx, (k_ntt_pass<1, 256, 1>), div_up(n_thr, 256), 256, 0, src, dst, W, log_n, s, last, scale, dsc, tab);
+        else if (R == 2) NZ_LAUNCH(ctx, (k_ntt_pass<2, 256, 1>), div_up(n_thr, 256), 256, 0, src, dst, W, log_n, s, last, scale, dsc, tab);
+        else if (variant == 0) NZ_LAUNCH(ctx, (k_ntt_pass<3, 256, 1>), div_up(n_thr, 256), 256, 0, src, dst, W, log_n, s, last, scale, dsc, tab);
+        else if (variant == 2) NZ_LAUNCH(ctx, (k_ntt_pass<3, 256, 2>), div_up(n_thr, 256), 256, 0, src, dst, W, log_n, s, last, scale, dsc, tab);
+        else if (variant == 3) NZ_LAUNCH(ctx, (k_ntt_pass<3, 128, 3>), div_up(n_thr, 128), 128, 0, src, dst, W, log_n, s, last, scale, dsc, tab);
+        else NZ_LAUNCH(ctx, (k_ntt_pass<3, 128, 4>), div_up(n_thr, 128), 128, 0, src, dst, W, log_n, s, last, scale, dsc, tab);
+        s += R;
+    }
+    if (n_pass == 1)  // a single launch cannot permute in place: it wrote tmp
+        NZ_CUDA(ctx, cudaMemcpyAsync(d, tmp, ((size_t)1 << log_n) * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->stream));
     return 0;
 }
 

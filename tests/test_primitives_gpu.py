@@ -19,7 +19,7 @@ def _fr_unbuf(buf):
     return [b.from_lem(buf[i:i + 32]) for i in range(0, len(buf), 32)]
 
 
-@pytest.mark.parametrize("log_n", [1, 2, 3, 4, 5, 6, 7, 9, 10, 12])
+@pytest.mark.parametrize("log_n", [1, 2, 3, 4, 5, 6, 7, 9, 10, 11, 12, 13, 14, 15])
 def test_ntt_matches_oracle(ctx, log_n):
     from nzcb_circom_b200.ffjavascript import Fr
 
@@ -33,7 +33,7 @@ def test_ntt_matches_oracle(ctx, log_n):
     assert got_i == ontt.ifft(vals)
 
 
-@pytest.mark.parametrize("log_n", [16, 20, 22])
+@pytest.mark.parametrize("log_n", [16, 17, 18, 19, 20, 21, 22, 23])
 def test_ntt_roundtrip_and_pointcheck_large(ctx, log_n):
     """iNTT(NTT(x)) == x bit-exact, and X[k] == sum_j x_j w^(jk) for a sparse x."""
     import numpy as np
