@@ -65,6 +65,13 @@ uint64_t nzcb_launch_count(const nzcb_ctx* ctx);
 /* milliseconds of device time of the last timed entry point (CUDA events on the ctx stream) */
 float nzcb_last_device_ms(const nzcb_ctx* ctx);
 
+/* Single-proof latency mode: `world` contexts (one per GPU / process) prove the SAME proof; each
+ * commits only its contiguous slice of the point range of every fixed-base MSM, and the partial sums (one 128-byte
+ * XYZZ point per commitment and rank) are exchanged through `allgather(user, send, recv, bytes)` -- recv receives
+ * world x bytes in rank order; the caller implements it with NCCL / P2P.  world = 1 turns the mode off. */
+int32_t nzcb_ctx_set_msm_split(nzcb_ctx* ctx, int32_t rank, int32_t world,
+                               int (*allgather)(void* user, const void* send, void* recv, size_t bytes), void* user);
+
 /* integer-pipe microbenchmark (roofline denominators): kind 0 = IMAD,
  * 1 = IMAD.WIDE.U32, 2 = Fr Montgomery multiply, 3 = Fq multiply, 4 = IMAD.HI.U32,
  * 5 = Fr multiply, portable CIOS variant; result in ops/s */
@@ -173,6 +180,9 @@ int32_t nzcb_plonk_fullprove_batch_dev(nzcb_ctx* ctx, const nzcb_circuit* c, con
  * algorithmic modmul count of those launches (160 per MSM point) and resets. */
 int32_t nzcb_profile(nzcb_ctx* ctx, int32_t enable);
 int32_t nzcb_profile_read(nzcb_ctx* ctx, uint64_t* launches, double* total_ms, double* alg_modmul);
+/* bucket additions (XYZZ += affine, 10 modmul each) the timed launches actually executed; read BEFORE
+ * nzcb_profile_read, which resets.  Smaller than the algorithmic count when scalars are small (round 1). */
+int32_t nzcb_profile_entries(nzcb_ctx* ctx, double* additions);
 
 #ifdef __cplusplus
 }

@@ -44,6 +44,7 @@ SIGNATURES = {
     "nzcb_last_error": (_cp, [_vp]),
     "nzcb_launch_count": (ctypes.c_uint64, [_vp]),
     "nzcb_last_device_ms": (ctypes.c_float, [_vp]),
+    "nzcb_ctx_set_msm_split": (_i32, [_vp, _i32, _i32, _vp, _vp]),
     "nzcb_microbench": (_i32, [_vp, _i32, _u32, _u32, ctypes.POINTER(ctypes.c_double)]),
     "nzcb_microbench_madd": (_i32, [_vp, _i32, _u32, _u32, ctypes.POINTER(ctypes.c_double)]),
     "nzcb_selftest_mul": (_i32, [_vp, _u32, ctypes.POINTER(ctypes.c_uint64)]),
@@ -76,6 +77,7 @@ SIGNATURES = {
     "nzcb_msm_g1_table_dev": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp]),
     "nzcb_g1_lagrange_basis": (_i32, [_vp, _vp, _u32, _vp]),
     "nzcb_profile": (_i32, [_vp, _i32]),
+    "nzcb_profile_entries": (_i32, [_vp, ctypes.POINTER(ctypes.c_double)]),
     "nzcb_profile_read": (_i32, [_vp, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_double),
                                  ctypes.POINTER(ctypes.c_double)]),
 }
@@ -132,6 +134,31 @@ class Context:
         except Exception:
             pass
 
+    ALLGATHER_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t)
+
+    def set_msm_split(self, rank, world, allgather=None):
+        """Latency mode: this ctx commits slice `rank` of `world` of every fixed-base MSM.  allgather(send: bytes) ->
+        bytes of all ranks in rank order (world x len(send)); None / world 1 switches the mode off."""
+        if world <= 1 or allgather is None:
+            self._split_cb = None
+            self.check(self.lib.nzcb_ctx_set_msm_split(self.h, 0, 1, None, None))
+            return
+
+        def _cb(_user, send, recv, nbytes):
+            try:
+                out = allgather(ctypes.string_at(send, nbytes))
+                if len(out) != world * nbytes:
+                    return 1
+                ctypes.memmove(recv, out, len(out))
+                return 0
+            except Exception:  # never unwind through the C frames
+                import traceback
+                traceback.print_exc()
+                return 1
+
+        self._split_cb = Context.ALLGATHER_FN(_cb)  # keep the thunk alive as long as the mode is on
+        self.check(self.lib.nzcb_ctx_set_msm_split(self.h, rank, world, ctypes.cast(self._split_cb, ctypes.c_void_p), None))
+
     def microbench(self, kind, iters=2000, blocks_per_sm=8):
         v = ctypes.c_double()
         self.check(self.lib.nzcb_microbench(self.h, kind, iters, blocks_per_sm, ctypes.byref(v)))
@@ -144,6 +171,12 @@ class Context:
 
     def profile(self, enable=True):
         self.check(self.lib.nzcb_profile(self.h, 1 if enable else 0))
+
+    def profile_entries(self):
+        """bucket additions actually executed by the timed launches (read before profile_read)"""
+        v = ctypes.c_double()
+        self.check(self.lib.nzcb_profile_entries(self.h, ctypes.byref(v)))
+        return v.value
 
     def profile_read(self):
         """(launches, total device ms, algorithmic modmul) of the MSM bucket-accumulation kernel"""

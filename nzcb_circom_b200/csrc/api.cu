@@ -99,6 +99,21 @@ extern "C" int32_t nzcb_profile(nzcb_ctx* ctx, int32_t enable) {
     for (nzcb_ctx* l : ctx->lanes) nzcb_profile(l, enable);
     return 0;
 }
+// bucket additions actually executed by the timed launches since the last read (call before nzcb_profile_read)
+extern "C" int32_t nzcb_profile_entries(nzcb_ctx* ctx, double* additions) {
+    if (!ctx || !additions) return NZCB_E_INVALID;
+    NZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    double n = 0;
+    for (size_t i = 0; i < ctx->prof_used && i < ctx->prof_entries.size(); i++) n += ctx->prof_entries[i];
+    for (nzcb_ctx* l : ctx->lanes) {
+        double ln = 0;
+        nzcb_profile_entries(l, &ln);
+        n += ln;
+    }
+    *additions = n;
+    return 0;
+}
+
 extern "C" int32_t nzcb_profile_read(nzcb_ctx* ctx, uint64_t* launches, double* total_ms, double* alg_modmul) {
     if (!ctx) return NZCB_E_INVALID;
     NZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

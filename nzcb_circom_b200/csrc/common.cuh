@@ -27,6 +27,11 @@ struct nzcb_ctx {
     std::mutex mu;                       // root only: guards the twiddle map
     int device = 0;
     int sm_count = 148;
+    // latency mode: this ctx commits only its slice of every fixed-base MSM; the partial sums of all
+    // ranks are exchanged through `split_allgather` (NCCL / P2P on the caller's side) and added up.  Root only.
+    int split_rank = 0, split_world = 1;
+    int (*split_allgather)(void* user, const void* send, void* recv, size_t bytes) = nullptr;
+    void* split_user = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float last_ms = 0.f;
@@ -37,6 +42,7 @@ struct nzcb_ctx {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_ev;
     size_t prof_used = 0;
     double prof_modmul = 0;  // algorithmic modmul of the timed launches (160 per MSM point)
+    std::vector<uint32_t> prof_entries;  // bucket additions actually executed per timed launch
     // twiddle tables per (log_n, inverse)
     std::map<uint32_t, nzcb::Fr*> twiddles;
     // grow-only scratch arenas keyed by name, so steady-state proving never mallocs
@@ -125,5 +131,7 @@ int msm_table_dev(nzcb_ctx* ctx, const G1Table& tab, const uint32_t* const* d_sc
 int g1_lagrange_basis(nzcb_ctx* ctx, const G1Affine* d_srs, uint32_t log_n, G1Affine* d_out);
 // D2H + stream sync + affine conversion of `count` <= 4 results
 int msm_to_host_affine(nzcb_ctx* ctx, const G1XYZZ* d_pt, G1Affine* h_out, int count = 1);
+// the same for results of msm_table_dev: in latency mode the ranks' partial sums are exchanged and added first
+int msm_table_finish(nzcb_ctx* ctx, const G1XYZZ* d_pt, G1Affine* h_out, int count);
 
 }  // namespace nzcb

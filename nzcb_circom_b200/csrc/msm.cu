@@ -32,6 +32,7 @@
 #include "common.cuh"
 #include <stdlib.h>
 #include <algorithm>
+#include <vector>
 
 namespace nzcb {
 
@@ -91,6 +92,7 @@ __device__ __forceinline__ uint32_t get_bits(const uint32_t* s, uint32_t off, ui
 constexpr int NZ_MSM_MAXJOBS = 4;
 struct DigitArgs {
     const uint32_t* scalars[NZ_MSM_MAXJOBS];
+    uint32_t lo[NZ_MSM_MAXJOBS];  // this ctx handles scalars [lo, n) of the job (latency mode: its slice)
     uint32_t n[NZ_MSM_MAXJOBS];
     uint32_t mont[NZ_MSM_MAXJOBS];
     uint32_t c, W, nbw, unified, stride;
@@ -146,7 +148,7 @@ template <bool COUNT>
 __global__ void __launch_bounds__(256) k_msm_digits(DigitArgs a, uint32_t* __restrict__ cnt,
                                                     const uint32_t* __restrict__ offsets, uint32_t* __restrict__ sorted) {
     const uint32_t k = blockIdx.y;
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t i = a.lo[k] + blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n[k]) return;
     for_each_digit(a, k, i, [&](uint32_t key, uint32_t ref) {
         if (COUNT) {
@@ -414,7 +416,7 @@ __global__ void k_set_inf(G1XYZZ* out, uint32_t n) {
 
 struct MsmJob {
     const uint32_t* scalars;
-    size_t n;
+    size_t lo, n;  // scalars [lo, n)
     bool mont;
 };
 
@@ -425,10 +427,11 @@ static int msm_run(nzcb_ctx* ctx, const G1Affine* d_bases, const MsmPlan& p, con
     for (int k = 0; k < K; k++) {
         if (jobs[k].n >= ((size_t)1 << 26)) return ctx->fail(NZCB_E_INVALID, "msm: n too large");
         da.scalars[k] = jobs[k].scalars;
+        da.lo[k] = (uint32_t)jobs[k].lo;
         da.n[k] = (uint32_t)jobs[k].n;
         da.mont[k] = jobs[k].mont ? 1 : 0;
-        n_max = std::max(n_max, jobs[k].n);
-        n_sum += jobs[k].n;
+        n_max = std::max(n_max, jobs[k].n - jobs[k].lo);
+        n_sum += jobs[k].n - jobs[k].lo;
     }
     da.c = p.c; da.W = p.W; da.nbw = p.nbw; da.unified = p.unified ? 1 : 0; da.stride = p.stride;
     const size_t n_keys = (size_t)p.G * p.nbw;
@@ -496,6 +499,9 @@ static int msm_run(nzcb_ctx* ctx, const G1Affine* d_bases, const MsmPlan& p, con
             NZ_CUDA(ctx, cudaEventCreate(&b));
             ctx->prof_ev.push_back({a, b});
         }
+        if (ctx->prof_entries.size() < 4096) ctx->prof_entries.resize(4096, 0);  // fixed storage: the copies below land here
+        if (ctx->prof_used < ctx->prof_entries.size())
+            NZ_CUDA(ctx, cudaMemcpyAsync(&ctx->prof_entries[ctx->prof_used], offsets + n_keys, 4, cudaMemcpyDeviceToHost, ctx->stream));
         NZ_CUDA(ctx, cudaEventRecord(ctx->prof_ev[ctx->prof_used].first, ctx->stream));
     }
     NZ_LAUNCH(ctx, k_msm_accum, acc_blocks, ACC_THREADS, 0, d_bases, sorted, offsets, (uint32_t)n_keys, L, chunk_bucket,
@@ -588,7 +594,13 @@ int msm_table_dev(nzcb_ctx* ctx, const G1Table& tab, const uint32_t* const* d_sc
     MsmJob jobs[NZ_MSM_MAXJOBS];
     for (int k = 0; k < K; k++) {
         if (n[k] > tab.n) return ctx->fail(NZCB_E_INVALID, "msm: %zu scalars for a table of %zu bases", n[k], tab.n);
-        jobs[k] = MsmJob{d_scalars[k], n[k], scalars_mont};
+        const nzcb_ctx* root = ctx->root();
+        size_t lo = 0, hi = n[k];
+        if (root->split_world > 1) {  // latency mode: contiguous slice of the point range
+            lo = n[k] * (size_t)root->split_rank / (size_t)root->split_world;
+            hi = n[k] * (size_t)(root->split_rank + 1) / (size_t)root->split_world;
+        }
+        jobs[k] = MsmJob{d_scalars[k], lo, hi, scalars_mont};
     }
     MsmPlan p;
     p.c = tab.c; p.W = tab.W; p.nbw = 1u << (tab.c - 1); p.G = (uint32_t)K; p.unified = true; p.stride = (uint32_t)tab.stride;
@@ -596,7 +608,7 @@ int msm_table_dev(nzcb_ctx* ctx, const G1Table& tab, const uint32_t* const* d_sc
 }
 
 int msm_dev(nzcb_ctx* ctx, const G1Affine* d_bases, const uint32_t* d_scalars, size_t n, bool mont, G1XYZZ* d_out) {
-    const MsmJob job{d_scalars, n, mont};
+    const MsmJob job{d_scalars, 0, n, mont};
     const MsmPlan p = make_plan_window(n, 1);
     return msm_run(ctx, d_bases, p, &job, 1, d_out);
 }
@@ -610,9 +622,38 @@ int msm_to_host_affine(nzcb_ctx* ctx, const G1XYZZ* d_pt, G1Affine* h_out, int c
     return 0;
 }
 
+int msm_table_finish(nzcb_ctx* ctx, const G1XYZZ* d_pt, G1Affine* h_out, int count) {
+    nzcb_ctx* root = ctx->root();
+    if (root->split_world <= 1) return msm_to_host_affine(ctx, d_pt, h_out, count);
+    if (count < 1 || count > NZ_MSM_MAXJOBS) return ctx->fail(NZCB_E_INVALID, "msm: bad point count");
+    if (!root->split_allgather) return ctx->fail(NZCB_E_INVALID, "msm split: no exchange function set");
+    G1XYZZ mine[NZ_MSM_MAXJOBS];
+    NZ_CUDA(ctx, cudaMemcpyAsync(mine, d_pt, (size_t)count * sizeof(G1XYZZ), cudaMemcpyDeviceToHost, ctx->stream));
+    NZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<G1XYZZ> all((size_t)root->split_world * count);
+    if (root->split_allgather(root->split_user, mine, all.data(), (size_t)count * sizeof(G1XYZZ)) != 0)
+        return ctx->fail(NZCB_E_CUDA, "msm split: the partial-sum exchange failed");
+    for (int k = 0; k < count; k++) {  // rank order is fixed, so every rank adds the same points in the same order
+        G1XYZZ acc = G1XYZZ::inf();
+        for (int r = 0; r < root->split_world; r++) acc.add(all[(size_t)r * count + k]);
+        h_out[k] = acc.to_affine();
+    }
+    return 0;
+}
+
 }  // namespace nzcb
 
 using namespace nzcb;
+
+extern "C" int32_t nzcb_ctx_set_msm_split(nzcb_ctx* ctx, int32_t rank, int32_t world,
+                                          int (*allgather)(void*, const void*, void*, size_t), void* user) {
+    if (!ctx || ctx->parent || world < 1 || rank < 0 || rank >= world || (world > 1 && !allgather)) return NZCB_E_INVALID;
+    ctx->split_rank = rank;
+    ctx->split_world = world;
+    ctx->split_allgather = allgather;
+    ctx->split_user = user;
+    return 0;
+}
 
 struct nzcb_g1_table {
     nzcb_ctx* ctx;
@@ -658,7 +699,7 @@ extern "C" int32_t nzcb_msm_g1_table_dev(nzcb_ctx* ctx, const nzcb_g1_table* t, 
     NZ_TRY(msm_table_dev(ctx, t->tab, (const uint32_t* const*)d_scalars, n, K, false, d_out));
     NZ_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     G1Affine a[NZ_MSM_MAXJOBS];
-    NZ_TRY(msm_to_host_affine(ctx, d_out, a, K));
+    NZ_TRY(msm_table_finish(ctx, d_out, a, K));
     cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1);
     memcpy(out, a, (size_t)K * 64);
     return 0;

@@ -718,7 +718,7 @@ int prove_core(nzcb_ctx* ctx, const nzcb_zkey* zk, const Fr* d_w_le, const uint8
         const size_t sn[3] = {(size_t)n + 4, (size_t)n + 4, (size_t)n + 4};
         G1Affine r[3];
         NZ_TRY(msm_table_dev(ctx, zk->tab_lag, sc, sn, 3, true, b.pts));
-        NZ_TRY(msm_to_host_affine(ctx, b.pts, r, 3));
+        NZ_TRY(msm_table_finish(ctx, b.pts, r, 3));
         cA = r[0]; cB = r[1]; cC = r[2];
     }
     g1_to_be(cA, out->A);
@@ -784,7 +784,7 @@ int prove_core(nzcb_ctx* ctx, const nzcb_zkey* zk, const Fr* d_w_le, const uint8
         const uint32_t* sc[1] = {(const uint32_t*)b.pol_z};
         const size_t sn[1] = {(size_t)n + 3};
         NZ_TRY(msm_table_dev(ctx, zk->tab, sc, sn, 1, true, b.pts));
-        NZ_TRY(msm_to_host_affine(ctx, b.pts, &cZ, 1));
+        NZ_TRY(msm_table_finish(ctx, b.pts, &cZ, 1));
     }
     g1_to_be(cZ, out->Z);
 
@@ -826,7 +826,7 @@ int prove_core(nzcb_ctx* ctx, const nzcb_zkey* zk, const Fr* d_w_le, const uint8
         const size_t sn[3] = {N, N, N + 6};
         G1Affine r[3];
         NZ_TRY(msm_table_dev(ctx, zk->tab, sc, sn, 3, true, b.pts));
-        NZ_TRY(msm_to_host_affine(ctx, b.pts, r, 3));
+        NZ_TRY(msm_table_finish(ctx, b.pts, r, 3));
         cT1 = r[0]; cT2 = r[1]; cT3 = r[2];
     }
     g1_to_be(cT1, out->T1);
@@ -915,7 +915,7 @@ int prove_core(nzcb_ctx* ctx, const nzcb_zkey* zk, const Fr* d_w_le, const uint8
         const size_t sn[2] = {N + 6, N + 3};
         G1Affine r[2];
         NZ_TRY(msm_table_dev(ctx, zk->tab, sc, sn, 2, true, b.pts));
-        NZ_TRY(msm_to_host_affine(ctx, b.pts, r, 2));
+        NZ_TRY(msm_table_finish(ctx, b.pts, r, 2));
         cWxi = r[0]; cWxiw = r[1];
     }
     tr_.mark("r5 rest");

@@ -24,3 +24,21 @@ def gather_results(local_results, n_items, rank, world, dist=None):
         for i, v in zip(shard_indices(n_items, r, world), part):
             out[i] = v
     return out
+
+
+def torch_allgather_bytes(dist, device=None):
+    """allgather callable for Context.set_msm_split on top of torch.distributed: NCCL over NVLink when `device` is a
+    CUDA device (the 128-byte partial sums of the latency mode), gloo otherwise."""
+    import torch
+
+    world = dist.get_world_size()
+
+    def allgather(send: bytes) -> bytes:
+        t = torch.frombuffer(bytearray(send), dtype=torch.uint8)
+        if device is not None:
+            t = t.to(device)
+        out = torch.empty(world * t.numel(), dtype=torch.uint8, device=t.device)
+        dist.all_gather_into_tensor(out, t)
+        return out.cpu().numpy().tobytes()
+
+    return allgather

@@ -666,3 +666,12 @@ int oracle_num_threads(void) {
     return 1;
 #endif
 }
+
+/* torchrun exports OMP_NUM_THREADS=1 to its ranks: the baseline legs ask for the host's cores explicitly */
+void oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}

@@ -43,6 +43,16 @@ def num_threads():
     return lib().oracle_num_threads()
 
 
+def use_all_cores():
+    """OpenMP threads = the cores this process may run on (torchrun sets OMP_NUM_THREADS=1 for its ranks)"""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    lib().oracle_set_num_threads(n)
+    return num_threads()
+
+
 def ntt(data_lem: bytes, inverse=False):
     n = len(data_lem) // 32
     buf = ctypes.create_string_buffer(data_lem, len(data_lem))

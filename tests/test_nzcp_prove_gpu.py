@@ -63,3 +63,59 @@ def test_nzcp_live_proofs_verify(nzcp_live_prover):
     assert st == [0]
     proof2, pub2 = plonk.prove(pr.zk, wtns_from_raw(raw), blinders=blinders[0], raw=True)
     assert proof2 == res[0][0] and pub2 == res[0][1]
+
+
+def test_msm_split_latency_mode_two_ranks_one_gpu(nzcp_live_prover):
+    """Latency mode: two contexts prove the SAME pass, each committing half of every MSM's point
+    range; the partial sums are exchanged (here: an in-process all-gather between two threads sharing the GPU;
+    bench.py does it with NCCL between processes) -- both ranks must emit the single-GPU proof byte for byte."""
+    import threading
+
+    from nzcb_circom_b200 import Context
+    from nzcb_circom_b200.prover import NzcpProver, default_tau
+
+    pr0 = nzcp_live_prover
+    p = H.synth_pass(21)
+    item = [(p["toBeSigned"], p["data"])]
+    rng = random.Random(9)
+    bl = [[rng.randrange(b.R_MOD) for _ in range(9)]]
+    expect = pr0.prove_passes(item, bl)[0]
+    assert expect[2] == 0
+
+    world = 2
+    barrier = threading.Barrier(world)
+    slots = [None] * world
+    results = [None] * world
+    errors = []
+
+    def make_allgather(rank):
+        def allgather(send):
+            slots[rank] = send
+            barrier.wait(timeout=120)
+            out = b"".join(slots)
+            barrier.wait(timeout=120)
+            return out
+        return allgather
+
+    def run(rank, prover):
+        try:
+            prover.ctx.set_msm_split(rank, world, make_allgather(rank))
+            results[rank] = prover.prove_passes(item, bl)[0]
+        except Exception as e:  # pragma: no cover
+            errors.append(e)
+            barrier.abort()
+        finally:
+            prover.ctx.set_msm_split(0, 1, None)
+
+    ctx1 = Context(0)
+    pr1 = NzcpProver(live=True, tau=default_tau(), ctx=ctx1)
+    pr1.setup()
+    th = [threading.Thread(target=run, args=(0, pr0)), threading.Thread(target=run, args=(1, pr1))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errors, errors
+    assert results[0] == expect and results[1] == expect
+    pr1.zk.close()
+    ctx1.close()
