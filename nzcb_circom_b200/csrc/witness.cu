@@ -16,6 +16,7 @@
 // falls back to a Fermat inverse otherwise.
 #include "common.cuh"
 #include <algorithm>
+#include <cuda_pipeline.h>
 
 using namespace nzcb;
 
@@ -31,6 +32,7 @@ struct nzcb_circuit {
     uint32_t* d_ioff = nullptr;  // instruction offsets; inside a level the long instructions come first
     uint32_t* d_lstart = nullptr;
     uint32_t* d_nlong = nullptr; // per level: how many leading instructions run one-per-warp
+    uint4* d_rec = nullptr;      // 128-byte records: a short instruction's whole encoding in one line (prefetched to smem)
     uint32_t* d_code = nullptr;
     Fr* d_invtab = nullptr;      // canonical 1/k, k = 0..NZ_INV_TAB (entry 0 unused)
 };
@@ -41,6 +43,7 @@ struct ProgView {
     const Fr* consts;      // Montgomery
     const Fr* consts_can;  // canonical
     const uint32_t *ioff, *lstart, *nlong, *code;
+    const uint4* rec;      // 8 x uint4 (128 B) per instruction, level order: the first 32 code words of each instruction
     const Fr* invtab;
     uint32_t n_total, n_out, n_in, n_levels;
 };
@@ -52,31 +55,52 @@ __device__ __forceinline__ bool fits_u32(const Fr& v) {
     return hi == 0;
 }
 
+// the multiply and the Fermat inverse of the rare paths (general coefficients, wide operands, operands outside
+// the inverse table) stay out of line: the interpreter is latency bound and its code should stay small
+__device__ __noinline__ Fr wit_mul(const Fr& a, const Fr& b) { return a * b; }
+__device__ __noinline__ Fr wit_inv(const Fr& v) { return v.to_mont().inv().from_mont(); }
+
 // acc += coef_c * v  for one LC term (canonical values; coefficient index c: 0 = +1, 1 = -1)
 __device__ __forceinline__ void lc_term(const ProgView& pv, Fr& acc, uint32_t c, const Fr& v) {
     if (c == 0) acc = acc + v;
     else if (c == 1) acc = acc - v;
     else if (v.is_zero()) return;
     else if (fits_u32(v) && v.v[0] == 1) acc = acc + pv.consts_can[c];  // bit wires: no multiply
-    else acc = acc + pv.consts[c] * v;  // Montgomery const x canonical wire = canonical
+    else acc = acc + wit_mul(pv.consts[c], v);  // Montgomery const x canonical wire = canonical
 }
 
+constexpr uint32_t WIT_THREADS = 256;
+constexpr uint32_t REC_WORDS = 32;
+constexpr uint32_t REC_LONG = 0x100u;  // flag on word 0: the encoding does not fit a record, word 1 = its code offset
+
+// where an instruction's words come from: the code stream in global memory, or this thread's record in shared
+// memory (word-major so that the threads of a warp read consecutive 16-byte groups)
+struct GlobalCode {
+    const uint32_t* code;
+    __device__ __forceinline__ uint32_t operator()(uint32_t p) const { return code[p]; }
+};
+struct SmemCode {
+    const uint32_t* base;  // &slot[0][thread] viewed as words
+    __device__ __forceinline__ uint32_t operator()(uint32_t k) const { return base[(k >> 2) * (WIT_THREADS * 4) + (k & 3)]; }
+};
+
 // canonical value of  k + sum coef_i * w_i ;  advances p past the encoded LC   (one thread)
-__device__ __forceinline__ Fr eval_lc(const ProgView& pv, const Fr* __restrict__ W, uint32_t& p) {
-    const uint32_t n = pv.code[p], ci = pv.code[p + 1];
+template <class RD>
+__device__ __forceinline__ Fr eval_lc(const ProgView& pv, const RD& rd, const Fr* __restrict__ W, uint32_t& p) {
+    const uint32_t n = rd(p), ci = rd(p + 1);
     p += 2;
     Fr acc = ci != 0xffffffffu ? pv.consts_can[ci] : Fr::zero();
     if (n == 0) return acc;
     // one term of lookahead: the next wire is in flight while this one is folded in
-    uint32_t w = pv.code[p], c = pv.code[p + 1];
+    uint32_t w = rd(p), c = rd(p + 1);
     Fr v = W[w];
     for (uint32_t t = 0; t < n; t++) {
         const uint32_t c_cur = c;
         const Fr v_cur = v;
         p += 2;
         if (t + 1 < n) {
-            w = pv.code[p];
-            c = pv.code[p + 1];
+            w = rd(p);
+            c = rd(p + 1);
             v = W[w];
         }
         lc_term(pv, acc, c_cur, v_cur);
@@ -90,9 +114,25 @@ __device__ __forceinline__ Fr eval_lc_warp(const ProgView& pv, const Fr* __restr
     const uint32_t n = pv.code[p], ci = pv.code[p + 1];
     p += 2;
     Fr acc = (ci != 0xffffffffu && lane == 0) ? pv.consts_can[ci] : Fr::zero();
-    for (uint32_t t = lane; t < n; t += 32) {
-        const uint32_t w = pv.code[p + 2 * t], c = pv.code[p + 2 * t + 1];
-        lc_term(pv, acc, c, W[w]);
+    // four terms per lane at a time: their code words leave together, then their wires -- two memory round trips
+    // per chunk instead of eight
+    for (uint32_t t0 = lane; t0 < n; t0 += 128) {
+        uint32_t w[4], c[4];
+        Fr v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t t = t0 + 32 * k;
+            if (t < n) {
+                w[k] = pv.code[p + 2 * t];
+                c[k] = pv.code[p + 2 * t + 1];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (t0 + 32 * k < n) v[k] = W[w[k]];
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (t0 + 32 * k < n) lc_term(pv, acc, c[k], v[k]);
     }
     p += 2 * n;
 #pragma unroll
@@ -118,7 +158,7 @@ __device__ __forceinline__ Fr mul_canonical(const Fr& a, const Fr& b) {
         o.v[1] = (uint32_t)(pr >> 32);
         return o;
     }
-    return (a * b) * Fr::r2();
+    return wit_mul(wit_mul(a, b), Fr::r2());
 }
 
 __device__ __forceinline__ Fr inv_or_zero(const ProgView& pv, const Fr& v) {
@@ -126,32 +166,30 @@ __device__ __forceinline__ Fr inv_or_zero(const ProgView& pv, const Fr& v) {
     if (fits_u32(v) && v.v[0] <= NZ_INV_TAB) return pv.invtab[v.v[0]];
     const Fr m = v.neg();
     if (fits_u32(m) && m.v[0] <= NZ_INV_TAB) return pv.invtab[m.v[0]].neg();  // 1/(-k) = -(1/k)
-    return v.to_mont().inv().from_mont();
+    return wit_inv(v);
 }
 
-constexpr uint32_t WIT_THREADS = 512;
-
-// Executes instruction i.  WARP: all 32 lanes cooperate on its LCs (lane 0 commits); else one thread.
-template <bool WARP>
-__device__ __forceinline__ bool exec_instr(const ProgView& pv, Fr* __restrict__ W, uint32_t i, uint32_t lane) {
-    uint32_t p = pv.ioff[i];
-    const uint32_t op = pv.code[p];
-    auto LC = [&](uint32_t& q) { return WARP ? eval_lc_warp(pv, W, q, lane) : eval_lc(pv, W, q); };
+// Executes the instruction whose words rd() serves from offset p.  WARP: all 32 lanes cooperate on its LCs (lane 0
+// commits; code stream only); else one thread.
+template <bool WARP, class RD>
+__device__ __forceinline__ bool exec_instr(const ProgView& pv, const RD& rd, Fr* __restrict__ W, uint32_t p, uint32_t lane) {
+    const uint32_t op = rd(p) & 0xffu;
+    auto LC = [&](uint32_t& q) { return WARP ? eval_lc_warp(pv, W, q, lane) : eval_lc(pv, rd, W, q); };
     const bool commit = !WARP || lane == 0;
     if (op == OP_LIN) {
-        const uint32_t dst = pv.code[p + 1];
+        const uint32_t dst = rd(p + 1);
         p += 2;
         const Fr v = LC(p);
         if (commit) W[dst] = v;
     } else if (op == OP_MUL) {
-        const uint32_t dst = pv.code[p + 1];
+        const uint32_t dst = rd(p + 1);
         p += 2;
         const Fr a = LC(p);
         const Fr b = LC(p);
         const Fr c = LC(p);
         if (commit) W[dst] = mul_canonical(a, b) + c;
     } else if (op == OP_BITS) {
-        const uint32_t dst = pv.code[p + 1], src = pv.code[p + 2], n = pv.code[p + 3];
+        const uint32_t dst = rd(p + 1), src = rd(p + 2), n = rd(p + 3);
         const Fr v = W[src];
         for (uint32_t k = WARP ? lane : 0; k < n; k += WARP ? 32 : 1) {
             Fr bit = Fr::zero();
@@ -159,7 +197,7 @@ __device__ __forceinline__ bool exec_instr(const ProgView& pv, Fr* __restrict__ 
             W[dst + k] = bit;
         }
     } else if (op == OP_INV) {
-        if (commit) W[pv.code[p + 1]] = inv_or_zero(pv, W[pv.code[p + 2]]);
+        if (commit) W[rd(p + 1)] = inv_or_zero(pv, W[rd(p + 2)]);
     } else {  // OP_ASSERT
         p += 1;
         const Fr a = LC(p);
@@ -170,11 +208,69 @@ __device__ __forceinline__ bool exec_instr(const ProgView& pv, Fr* __restrict__ 
     return false;
 }
 
+// LIN / MUL / ASSERT whose whole encoding sits in this thread's shared-memory record: every wire the instruction
+// reads is requested before the first one is used, so the three LCs of a product cost one memory round trip, not
+// three.  (BITS / INV and anything longer go through exec_instr.)
+__device__ __forceinline__ bool exec_short(const ProgView& pv, const SmemCode& rd, Fr* __restrict__ W, uint32_t op) {
+    const uint32_t base_a = (op == OP_ASSERT ? 1u : 2u) + 2u;  // first term word of LC A
+    const uint32_t na = rd(base_a - 2), ci_a = rd(base_a - 1);
+    uint32_t nb = 0, nc = 0, ci_b = 0xffffffffu, ci_c = 0xffffffffu;
+    if (op != OP_LIN) {
+        const uint32_t hb = base_a + 2 * na;
+        nb = rd(hb);
+        ci_b = rd(hb + 1);
+        const uint32_t hc = hb + 2 + 2 * nb;
+        nc = rd(hc);
+        ci_c = rd(hc + 1);
+    }
+    const uint32_t nab = na + nb, nt = nab + nc;
+    auto pos = [&](uint32_t t) { return base_a + 2 * t + (t >= na ? 2u : 0u) + (t >= nab ? 2u : 0u); };
+    constexpr int BATCH = 4;
+    Fr v[BATCH];
+#pragma unroll
+    for (int k = 0; k < BATCH; k++)
+        if ((uint32_t)k < nt) v[k] = W[rd(pos(k))];
+    Fr A = ci_a != 0xffffffffu ? pv.consts_can[ci_a] : Fr::zero();
+    Fr Bv = ci_b != 0xffffffffu ? pv.consts_can[ci_b] : Fr::zero();
+    Fr Cv = ci_c != 0xffffffffu ? pv.consts_can[ci_c] : Fr::zero();
+    auto fold = [&](uint32_t t, const Fr& x) {
+        const uint32_t c = rd(pos(t) + 1);
+        if (t < na) lc_term(pv, A, c, x);
+        else if (t < nab) lc_term(pv, Bv, c, x);
+        else lc_term(pv, Cv, c, x);
+    };
+#pragma unroll
+    for (int k = 0; k < BATCH; k++)
+        if ((uint32_t)k < nt) fold(k, v[k]);
+    for (uint32_t t = BATCH; t < nt; t++) fold(t, W[rd(pos(t))]);
+    if (op == OP_LIN) {
+        W[rd(1)] = A;
+        return false;
+    }
+    const Fr ab = mul_canonical(A, Bv);
+    if (op == OP_MUL) {
+        W[rd(1)] = ab + Cv;
+        return false;
+    }
+    return ab != Cv;  // OP_ASSERT
+}
+
 // One CTA per pass.  Within a level the host has put the "long" instructions (many LC terms, or wide bit
-// decompositions) first: those run one per warp, the rest one per thread.
+// decompositions) first: those run one per warp from the code stream.  The rest run one per thread; the encoding of
+// the instruction a thread will execute in the NEXT level is copied asynchronously (cp.async) from the flat record
+// array into its shared-memory slot while the current level runs, so a level's critical path is wire loads,
+// arithmetic, store, barrier -- no instruction fetch.
 __global__ void __launch_bounds__(WIT_THREADS) k_witness(ProgView pv, const Fr* __restrict__ inputs, Fr* __restrict__ wires,
                                                          int32_t* __restrict__ status, uint32_t B) {
+    extern __shared__ uint4 s_rec[];  // [2][8][WIT_THREADS]
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = WIT_THREADS / 32;
+    const GlobalCode gcode{pv.code};
+    auto slot = [&](uint32_t buf, uint32_t k8) { return s_rec + ((size_t)buf * 8 + k8) * WIT_THREADS + threadIdx.x; };
+    auto prefetch = [&](uint32_t buf, uint32_t i) {
+        const uint4* src = pv.rec + (size_t)i * 8;
+#pragma unroll
+        for (uint32_t k8 = 0; k8 < 8; k8++) __pipeline_memcpy_async(slot(buf, k8), src + k8, 16);
+    };
     for (uint32_t pass = blockIdx.x; pass < B; pass += gridDim.x) {
         Fr* W = wires + (size_t)pass * pv.n_total;
         const Fr* in = inputs + (size_t)pass * pv.n_in;
@@ -184,23 +280,38 @@ __global__ void __launch_bounds__(WIT_THREADS) k_witness(ProgView pv, const Fr* 
             one.v[0] = 1;
             W[0] = one;
         }
-        __syncthreads();
         bool failed = false;
         uint32_t lo = pv.lstart[0], hi = pv.n_levels ? pv.lstart[1] : 0, nl = pv.n_levels ? pv.nlong[0] : 0;
+        if (lo + nl + threadIdx.x < hi) prefetch(0, lo + nl + threadIdx.x);
+        __pipeline_commit();
+        __syncthreads();
         for (uint32_t l = 0; l < pv.n_levels; l++) {
-            // next level's bounds are fetched while this one executes
+            const uint32_t buf = l & 1;
+            // next level's bounds, and this thread's instruction of it, are fetched while this level executes
             uint32_t hi_n = 0, nl_n = 0;
             if (l + 1 < pv.n_levels) {
                 hi_n = pv.lstart[l + 2];
                 nl_n = pv.nlong[l + 1];
             }
-            for (uint32_t i = lo + warp; i < lo + nl; i += n_warps) failed |= exec_instr<true>(pv, W, i, lane);
-            for (uint32_t i = lo + nl + threadIdx.x; i < hi; i += WIT_THREADS) failed |= exec_instr<false>(pv, W, i, lane);
+            if (hi + nl_n + threadIdx.x < hi_n) prefetch(buf ^ 1, hi + nl_n + threadIdx.x);
+            __pipeline_commit();
+            for (uint32_t i = lo + warp; i < lo + nl; i += n_warps) failed |= exec_instr<true>(pv, gcode, W, pv.ioff[i], lane);
+            uint32_t i = lo + nl + threadIdx.x;
+            if (i < hi) {
+                __pipeline_wait_prior(1);  // everything but the copy just issued has landed: this level's record
+                const SmemCode scode{reinterpret_cast<const uint32_t*>(slot(buf, 0))};
+                const uint32_t w0 = scode(0), op = w0 & 0xffu;
+                if (w0 & REC_LONG) failed |= exec_instr<false>(pv, gcode, W, scode(1), lane);
+                else if (op == OP_BITS || op == OP_INV) failed |= exec_instr<false>(pv, scode, W, 0, lane);
+                else failed |= exec_short(pv, scode, W, op);
+                for (i += WIT_THREADS; i < hi; i += WIT_THREADS) failed |= exec_instr<false>(pv, gcode, W, pv.ioff[i], lane);
+            }
             __syncthreads();
             lo = hi;
             hi = hi_n;
             nl = nl_n;
         }
+        __pipeline_wait_prior(0);
         if (failed) atomicExch(&status[pass], NZCB_E_ASSERT);
         __syncthreads();
     }
@@ -228,6 +339,7 @@ extern "C" void nzcb_circuit_free(nzcb_circuit* c) {
     cudaFree(c->d_consts);
     cudaFree(c->d_consts_can);
     cudaFree(c->d_nlong);
+    cudaFree(c->d_rec);
     cudaFree(c->d_ioff);
     cudaFree(c->d_lstart);
     cudaFree(c->d_code);
@@ -275,7 +387,7 @@ extern "C" int32_t nzcb_circuit_load(nzcb_ctx* ctx, const uint8_t* data, size_t 
     const uint8_t* p_lstart = p_ioff + (size_t)c->n_instr * 4;
     const uint8_t* p_code = p_lstart + ((size_t)c->n_levels + 1) * 4;
     // validate once on the host so the kernel can trust every index; measure every instruction
-    std::vector<uint32_t> ioff_sorted(c->n_instr), nlong(std::max<uint32_t>(1, c->n_levels), 0);
+    std::vector<uint32_t> ioff_sorted(c->n_instr), nlong(std::max<uint32_t>(1, c->n_levels), 0), recs;
     {
         std::vector<uint32_t> code(c->n_code), ioff(c->n_instr), ls(c->n_levels + 1), weight(c->n_instr, 0);
         memcpy(code.data(), p_code, (size_t)c->n_code * 4);
@@ -331,11 +443,34 @@ extern "C" int32_t nzcb_circuit_load(nzcb_ctx* ctx, const uint8_t* data, size_t 
             }
             nlong[l] = nl;
         }
+        // flat records, level order: an instruction's own words if they fit, else a pointer into the code stream
+        recs.assign((size_t)std::max<uint32_t>(1, c->n_instr) * REC_WORDS, 0);
+        for (uint32_t k = 0; k < c->n_instr; k++) {
+            uint32_t* r = &recs[(size_t)k * REC_WORDS];
+            const uint32_t p = ioff_sorted[k];
+            const uint32_t op = code[p];
+            uint32_t len;
+            if (op == OP_BITS) len = 4;
+            else if (op == OP_INV) len = 3;
+            else {
+                uint32_t q = p + (op == OP_ASSERT ? 1 : 2);
+                for (uint32_t j = 0; j < (op == OP_LIN ? 1u : 3u); j++) q += 2 + 2 * code[q];
+                len = q - p;
+            }
+            if (len <= REC_WORDS) {
+                for (uint32_t j = 0; j < len; j++) r[j] = code[p + j];
+            } else {
+                r[0] = op | REC_LONG;
+                r[1] = p;
+            }
+        }
     }
     WC_CUDA(cudaSetDevice(ctx->device));
     WC_CUDA(cudaMalloc(&c->d_consts, (size_t)c->n_consts * 32));
     WC_CUDA(cudaMalloc(&c->d_consts_can, (size_t)c->n_consts * 32));
     WC_CUDA(cudaMalloc(&c->d_nlong, nlong.size() * 4));
+    WC_CUDA(cudaMalloc(&c->d_rec, recs.size() * 4));
+    WC_CUDA(cudaMemcpyAsync(c->d_rec, recs.data(), recs.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
     WC_CUDA(cudaMemcpyAsync(c->d_consts_can, p_consts, (size_t)c->n_consts * 32, cudaMemcpyHostToDevice, ctx->stream));
     WC_CUDA(cudaMemcpyAsync(c->d_nlong, nlong.data(), nlong.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
     WC_CUDA(cudaMalloc(&c->d_ioff, std::max<size_t>(4, (size_t)c->n_instr * 4)));
@@ -360,11 +495,16 @@ namespace nzcb {
 int witness_dev(nzcb_ctx* ctx, const nzcb_circuit* c, const Fr* d_inputs, size_t B, Fr* d_wires, int32_t* d_status) {
     ProgView pv;
     pv.consts = c->d_consts; pv.consts_can = c->d_consts_can; pv.ioff = c->d_ioff; pv.lstart = c->d_lstart;
-    pv.nlong = c->d_nlong; pv.code = c->d_code; pv.invtab = c->d_invtab;
+    pv.nlong = c->d_nlong; pv.code = c->d_code; pv.invtab = c->d_invtab; pv.rec = c->d_rec;
     pv.n_total = c->n_total; pv.n_out = c->n_out; pv.n_in = c->n_in; pv.n_levels = c->n_levels;
     NZ_CUDA(ctx, cudaMemsetAsync(d_status, 0, B * sizeof(int32_t), ctx->stream));
     const uint32_t grid = (uint32_t)std::min<size_t>(B, (size_t)ctx->sm_count * 8);
-    NZ_LAUNCH(ctx, k_witness, grid, WIT_THREADS, 0, pv, d_inputs, d_wires, d_status, (uint32_t)B);
+    constexpr size_t smem = (size_t)2 * 8 * WIT_THREADS * sizeof(uint4);
+    static const bool attr_set = [] {
+        return cudaFuncSetAttribute(k_witness, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess;
+    }();
+    if (!attr_set) return ctx->fail(NZCB_E_CUDA, "witness: cannot reserve %zu bytes of shared memory", smem);
+    NZ_LAUNCH(ctx, k_witness, grid, WIT_THREADS, smem, pv, d_inputs, d_wires, d_status, (uint32_t)B);
     return 0;
 }
 uint32_t circuit_n_total(const nzcb_circuit* c) { return c->n_total; }
