@@ -365,6 +365,32 @@ __global__ void __launch_bounds__(128) k_seg_level(const uint32_t* __restrict__ 
     }
 }
 
+// Short runs first: almost every bucket that straddles a chunk boundary has two or three partials.  One thread per
+// list entry; the thread at the head of a run of at most SEG_SHORT equal keys adds it up and completes the bucket.
+// The keys of resolved entries are blanked in a second array, which the level-by-level reduction above then
+// processes -- it only finds work when a bucket holds a large share of all points.
+constexpr uint32_t SEG_SHORT = 6;
+__global__ void __launch_bounds__(128) k_seg_join(const uint32_t* __restrict__ keys, const G1XYZZ* __restrict__ vals, uint32_t N,
+                                                  G1XYZZ* __restrict__ buckets, uint32_t* __restrict__ okeys) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const uint32_t key = keys[i];
+    if (key == KEY_NONE) {
+        okeys[i] = KEY_NONE;
+        return;
+    }
+    // position inside the run and run length, both capped just above SEG_SHORT
+    uint32_t before = 0, after = 0;
+    while (before <= SEG_SHORT && i > before && keys[i - before - 1] == key) before++;
+    while (after <= SEG_SHORT && i + after + 1 < N && keys[i + after + 1] == key) after++;
+    const bool is_short = before + after + 1 <= SEG_SHORT;
+    okeys[i] = is_short ? KEY_NONE : key;
+    if (!is_short || before != 0) return;
+    G1XYZZ acc = vals[i];
+    for (uint32_t k = 1; k <= after; k++) acc.add(vals[i + k]);
+    buckets[key] = acc;
+}
+
 // ---- step 5: R(X) = sum_b weight(b) X_b per bucket set, weight = b + 1 (one_based) or b -------
 // chunk ch of S = 2^log_S elements: run = sum X, acc = sum local_weight * X (+ the chunk's plain sums P);
 // R(X) = sum_ch acc_ch + R0(S * run)  ->  Xo[ch] = S * run_ch (zero-based next level), Po[ch] = acc_ch + sum P.
@@ -391,6 +417,27 @@ __global__ void __launch_bounds__(128) k_bred(const G1XYZZ* __restrict__ X, cons
     Po[t] = acc;
     for (uint32_t i = 0; i < log_S; i++) run = run.dbl();
     Xo[t] = run;
+}
+
+// The later levels of the same recursion are small and latency bound (one point addition is ~10 us of dependent
+// multiplies), so they halve the array per launch with the two independent chains of a pair on different warps:
+// the first half of the grid computes Xo[i] = 2 (X[2i] + X[2i+1]), the second Po[i] = P[2i] + P[2i+1] + X[2i+1]
+// (zero-based weights: 0 * X[2i] + 1 * X[2i+1]).
+__global__ void __launch_bounds__(128) k_bred_pair(const G1XYZZ* __restrict__ X, const G1XYZZ* __restrict__ P, uint32_t pairs,
+                                                   uint32_t role_blocks, G1XYZZ* __restrict__ Xo, G1XYZZ* __restrict__ Po) {
+    const bool second = blockIdx.x >= role_blocks;
+    const uint32_t i = (second ? blockIdx.x - role_blocks : blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= pairs) return;
+    if (!second) {
+        G1XYZZ r = X[2 * (size_t)i];
+        r.add(X[2 * (size_t)i + 1]);
+        Xo[i] = r.dbl();
+    } else {
+        G1XYZZ q = P[2 * (size_t)i];
+        q.add(P[2 * (size_t)i + 1]);
+        q.add(X[2 * (size_t)i + 1]);
+        Po[i] = q;
+    }
 }
 
 // window mode: job k's result = sum_w 2^(c w) * set[k*W + w]   (Horner, one thread per job)
@@ -511,18 +558,18 @@ static int msm_run(nzcb_ctx* ctx, const G1Affine* d_bases, const MsmPlan& p, con
         ctx->prof_used++;
         ctx->prof_modmul += 160.0 * (double)n_sum;
     }
+    NZ_LAUNCH(ctx, k_seg_join, div_up((size_t)2 * T1, 128), 128, 0, pk0, pv0, 2 * T1, buckets, pk1);
     {
         uint32_t N = 2 * T1;
-        uint32_t *ki = pk0, *ko = pk1;
+        uint32_t *ki = pk1, *ko = pk0;  // the join wrote the surviving keys to pk1; the values stay in pv0
         G1XYZZ *vi = pv0, *vo = pv1;
-        uint32_t SL = 8;  // list entries per thread at this level
+        const uint32_t SL = 16;  // list entries per thread and level
         while (N > 32) {
             const uint32_t threads = (N + SL - 1) / SL;
             NZ_LAUNCH(ctx, k_seg_level, div_up(threads, 128), 128, 0, ki, vi, N, SL, buckets, ko, vo, 0);
             N = 2 * threads;
             std::swap(ki, ko);
             std::swap(vi, vo);
-            SL = 32;
         }
         NZ_LAUNCH(ctx, k_seg_level, 1, 32, 0, ki, vi, N, N, buckets, ko, vo, 1);
     }
@@ -534,15 +581,22 @@ static int msm_run(nzcb_ctx* ctx, const G1Affine* d_bases, const MsmPlan& p, con
     uint32_t bits = p.c - 1;  // log2 of the per-set length
     int one_based = 1;
     while (bits > 0) {
-        const uint32_t log_S = bits >= 3 ? 3 : bits;
-        bits -= log_S;
-        const uint32_t total = p.G << bits;
-        NZ_LAUNCH(ctx, k_bred, div_up(total, 128), 128, 0, X, P, total, log_S, one_based, xo, po);
+        if (one_based) {  // first level: every bucket, throughput bound -- serial running sums over chunks of 8
+            const uint32_t log_S = bits >= 3 ? 3 : bits;
+            bits -= log_S;
+            const uint32_t total = p.G << bits;
+            NZ_LAUNCH(ctx, k_bred, div_up(total, 128), 128, 0, X, P, total, log_S, one_based, xo, po);
+            one_based = 0;
+        } else {          // the rest: latency bound -- halve per launch
+            bits -= 1;
+            const uint32_t pairs = p.G << bits;
+            const uint32_t rb = div_up(pairs, 128);
+            NZ_LAUNCH(ctx, k_bred_pair, 2 * rb, 128, 0, X, P, pairs, rb, xo, po);
+        }
         X = xo;
         P = po;
         std::swap(xo, xo2);
         std::swap(po, po2);
-        one_based = 0;
     }
     // now P[g] = set g's weighted sum (c == 1 cannot happen: c >= 2)
     if (p.unified) {
