@@ -122,7 +122,9 @@ struct G1Table {
     size_t n = 0, stride = 0;
     uint32_t c = 0, W = 0;
 };
-int g1_table_build(nzcb_ctx* ctx, const G1Affine* d_bases, size_t n, G1Table* out);
+// window = 0: chosen from n (20 bits at 2^21: few digits, many buckets -- right for dense scalars);
+// a smaller window trades digits for buckets (sparse / small scalars: the reduction over empty buckets dominates)
+int g1_table_build(nzcb_ctx* ctx, const G1Affine* d_bases, size_t n, G1Table* out, uint32_t window = 0);
 void g1_table_free(G1Table* t);
 // K <= 4 MSMs over the first n[k] bases of one table as a single batch; results in d_out[0..K)
 int msm_table_dev(nzcb_ctx* ctx, const G1Table& tab, const uint32_t* const* d_scalars, const size_t* n, int K,

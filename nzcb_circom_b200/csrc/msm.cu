@@ -110,18 +110,30 @@ __device__ __forceinline__ bool above_half(const Fr& s) {
     return false;
 }
 
-// Signed-digit recode of scalar i of job k; calls f(bucket key, point reference | sign << 31) per non-zero digit.
-template <class F>
-__device__ __forceinline__ void for_each_digit(const DigitArgs& a, uint32_t k, uint32_t i, F f) {
-    Fr s = reinterpret_cast<const Fr*>(a.scalars[k])[i];
-    if (a.mont[k]) {
-        s = s.from_mont();
-    } else {
-        // multiExpAffine takes plain 256-bit integers: s * P = (s mod r) * P, and 2^256 < 6 r
-        for (int it = 0; it < 5; it++) s = Fr::reduce_once(s);
+// COUNT: histogram into cnt.   !COUNT: scatter, cnt is the per-bucket cursor (zeroed), offsets the scan.
+// Signed-digit recode of one scalar per thread; the digit loop is warp uniform so that lanes holding the SAME bucket
+// key (wire values are mostly 0 / +-1 / bytes in round 1) combine their atomics: one atomicAdd per distinct key
+// and warp, the lanes of a group take consecutive slots.
+template <bool COUNT>
+__global__ void __launch_bounds__(256) k_msm_digits(DigitArgs a, uint32_t* __restrict__ cnt,
+                                                    const uint32_t* __restrict__ offsets, uint32_t* __restrict__ sorted) {
+    const uint32_t k = blockIdx.y;
+    const uint32_t i = a.lo[k] + blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31;
+    bool live = i < a.n[k];
+    Fr s = Fr::zero();
+    if (live) {
+        s = reinterpret_cast<const Fr*>(a.scalars[k])[i];
+        if (a.mont[k]) {
+            s = s.from_mont();
+        } else {
+            // multiExpAffine takes plain 256-bit integers: s * P = (s mod r) * P, and 2^256 < 6 r
+            for (int it = 0; it < 5; it++) s = Fr::reduce_once(s);
+        }
+        live = !s.is_zero();
     }
-    if (s.is_zero()) return;
-    const bool neg = above_half(s);
+    if (__ballot_sync(0xffffffffu, live) == 0) return;
+    const bool neg = live && above_half(s);
     if (neg) s = Fr::modulus() - s;
     uint32_t carry = 0;
     const uint32_t half = 1u << (a.c - 1);
@@ -135,29 +147,22 @@ __device__ __forceinline__ void for_each_digit(const DigitArgs& a, uint32_t k, u
         } else {
             carry = 0;
         }
-        if (d) {
-            const uint32_t set = a.unified ? k : k * a.W + w;
+        const bool has = live && d != 0;
+        const uint32_t active = __ballot_sync(0xffffffffu, has);
+        if (!has) continue;  // the lanes with a digit stay converged on `active`
+        const uint32_t set = a.unified ? k : k * a.W + w;
+        const uint32_t key = set * a.nbw + (d - 1);
+        const uint32_t peers = __match_any_sync(active, key);
+        const uint32_t leader = __ffs(peers) - 1;
+        const uint32_t rank = __popc(peers & ((1u << lane) - 1));
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(&cnt[key], (uint32_t)__popc(peers));
+        if (!COUNT) {
+            base = __shfl_sync(peers, base, leader);
             const uint32_t ref = a.unified ? w * a.stride + i : i;
-            f(set * a.nbw + (d - 1), ref | ((neg != dneg) ? 0x80000000u : 0u));
+            sorted[offsets[key] + base + rank] = ref | ((neg != dneg) ? 0x80000000u : 0u);
         }
     }
-}
-
-// COUNT: histogram into cnt.   !COUNT: scatter, cnt is the per-bucket cursor (zeroed), offsets the scan.
-template <bool COUNT>
-__global__ void __launch_bounds__(256) k_msm_digits(DigitArgs a, uint32_t* __restrict__ cnt,
-                                                    const uint32_t* __restrict__ offsets, uint32_t* __restrict__ sorted) {
-    const uint32_t k = blockIdx.y;
-    const uint32_t i = a.lo[k] + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n[k]) return;
-    for_each_digit(a, k, i, [&](uint32_t key, uint32_t ref) {
-        if (COUNT) {
-            atomicAdd(&cnt[key], 1u);
-        } else {
-            const uint32_t pos = atomicAdd(&cnt[key], 1u);
-            sorted[offsets[key] + pos] = ref;
-        }
-    });
 }
 
 // ---- exclusive scan of n u32 counts into offsets[0..n], offsets[n] = total ------------------
@@ -621,11 +626,11 @@ __global__ void __launch_bounds__(128) k_table_build(const G1Affine* __restrict_
     }
 }
 
-int g1_table_build(nzcb_ctx* ctx, const G1Affine* d_bases, size_t n, G1Table* out) {
+int g1_table_build(nzcb_ctx* ctx, const G1Affine* d_bases, size_t n, G1Table* out, uint32_t window) {
     if (n == 0 || n >= ((size_t)1 << 26)) return ctx->fail(NZCB_E_INVALID, "g1 table: bad size %zu", n);
     out->n = n;
     out->stride = n;
-    out->c = msm_table_window(n);
+    out->c = window ? window : msm_table_window(n);
     out->W = 254 / out->c + 1;
     if ((size_t)out->W * n >= ((size_t)1 << 31)) return ctx->fail(NZCB_E_INVALID, "g1 table: too many points");
     if (cudaMalloc(&out->pts, (size_t)out->W * n * sizeof(G1Affine)) != cudaSuccess) {

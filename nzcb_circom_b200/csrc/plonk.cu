@@ -429,7 +429,14 @@ extern "C" int32_t nzcb_zkey_load(nzcb_ctx* ctx, const uint8_t* data, size_t len
                                     ctx->stream) != cudaSuccess)
                     rc = ctx->fail(NZCB_E_CUDA, "zkey: copy of the blinding bases failed");
         }
-        if (rc == 0) rc = g1_table_build(ctx, d_lagpts, n + 4, &zk->tab_lag);
+        // wire values are mostly 0 / +-1 / bytes: few digits whatever the window, so a 14-bit window (8 K buckets
+        // per commitment instead of 512 K) keeps the bucket reduction from dominating round 1
+        if (rc == 0) {
+            uint32_t c_lag = zk->power > 15 ? 14 : 0;
+            const char* env = getenv("NZCB_MSM_LAGRANGE_WINDOW");
+            if (env && atoi(env) >= 4 && atoi(env) <= 20) c_lag = (uint32_t)atoi(env);
+            rc = g1_table_build(ctx, d_lagpts, n + 4, &zk->tab_lag, c_lag);
+        }
         if (rc != 0) {
             nzcb_zkey_free(zk);
             return rc;
