@@ -222,8 +222,9 @@ extern "C" int32_t nzcb_microbench_madd(nzcb_ctx* ctx, int32_t variant, uint32_t
     if (variant == 2) bps = 3;
     if (variant == 3) { threads = 256; bps = 2; }
     if (variant == 4) { threads = 256; bps = 3; }
-    if (variant == 6) bps = 5;
-    if (variant == 7) { threads = 256; bps = 2; }
+    if (variant == 5) bps = 5;
+    if (variant == 6) bps = 6;
+    if (variant == 7) bps = 8;
     const uint32_t grid = (uint32_t)ctx->sm_count * bps;
     uint32_t* d = (uint32_t*)ctx->scratch_get("microbench", (size_t)grid * threads * 4);
     if (!d) return ctx->fail(NZCB_E_NOMEM, "microbench: out of memory");
@@ -235,9 +236,9 @@ extern "C" int32_t nzcb_microbench_madd(nzcb_ctx* ctx, int32_t variant, uint32_t
             case 2: NZ_LAUNCH(ctx, (k_madd_bench<MulInline, 128, 3>), grid, threads, 0, tab, n - 1, iters, d); break;
             case 3: NZ_LAUNCH(ctx, (k_madd_bench<MulInline, 256, 2>), grid, threads, 0, tab, n - 1, iters, d); break;
             case 4: NZ_LAUNCH(ctx, (k_madd_bench<MulCall, 256, 3>), grid, threads, 0, tab, n - 1, iters, d); break;
-            case 5: NZ_LAUNCH(ctx, (k_madd_bench<MulRolled, 128, 4>), grid, threads, 0, tab, n - 1, iters, d); break;
-            case 6: NZ_LAUNCH(ctx, (k_madd_bench<MulRolled, 128, 5>), grid, threads, 0, tab, n - 1, iters, d); break;
-            default: NZ_LAUNCH(ctx, (k_madd_bench<MulRolled, 256, 2>), grid, threads, 0, tab, n - 1, iters, d); break;
+            case 5: NZ_LAUNCH(ctx, (k_madd_bench<MulInline, 128, 5>), grid, threads, 0, tab, n - 1, iters, d); break;
+            case 6: NZ_LAUNCH(ctx, (k_madd_bench<MulInline, 128, 6>), grid, threads, 0, tab, n - 1, iters, d); break;
+            default: NZ_LAUNCH(ctx, (k_madd_bench<MulInline, 128, 8>), grid, threads, 0, tab, n - 1, iters, d); break;
         }
         NZ_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
         NZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

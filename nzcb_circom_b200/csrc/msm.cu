@@ -245,7 +245,7 @@ static int scan_excl(nzcb_ctx* ctx, const uint32_t* counts, uint32_t* offsets, s
 // balance whatever shares the GPU with it (other lanes' kernels, the witness program).
 // Per chunk: two (key, partial) slots for its first and last bucket (possibly shared with the neighbours);
 // every other bucket it meets lies wholly inside the chunk and is written straight to buckets[].
-constexpr uint32_t ACC_THREADS = 128, ACC_LMIN = 8, ACC_LMAX = 64;
+constexpr uint32_t ACC_THREADS = 256, ACC_LMIN = 8, ACC_LMAX = 64;
 
 // bucket holding the first entry of every chunk (binary search in the offsets, off the hot kernel's critical path)
 __global__ void __launch_bounds__(256) k_msm_chunk_buckets(const uint32_t* __restrict__ offsets, uint32_t n_keys, uint32_t L,
@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(256) k_msm_chunk_buckets(const uint32_t* __res
     chunk_bucket[ch] = b;
 }
 
-__global__ void __launch_bounds__(ACC_THREADS, 4)
+__global__ void __launch_bounds__(ACC_THREADS, 2)
     k_msm_accum(const G1Affine* __restrict__ bases, const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ offsets,
                 uint32_t n_keys, uint32_t L, const uint32_t* __restrict__ chunk_bucket, uint32_t* __restrict__ tile_counter,
                 G1XYZZ* __restrict__ buckets, uint32_t* __restrict__ pkeys, G1XYZZ* __restrict__ pvals) {

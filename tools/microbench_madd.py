@@ -3,7 +3,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from nzcb_circom_b200 import Context
 c = Context(0)
 res = {}
-names = {0: "inline 128x4", 1: "call 128x4", 2: "inline 128x3", 3: "inline 256x2", 4: "call 256x3", 5: "rolled 128x4", 6: "rolled 128x5", 7: "rolled 256x2"}
+names = {0: "inline 128x4", 1: "call 128x4", 2: "inline 128x3", 3: "inline 256x2", 4: "call 256x3", 5: "inline 128x5", 6: "inline 128x6", 7: "inline 128x8"}
 fq = c.microbench(3, 1000, 8)
 print(f"fq_mul peak {fq:.4e}/s")
 for log_table in (10,):
