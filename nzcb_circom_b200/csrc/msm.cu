@@ -7,8 +7,8 @@
 // flipped, so small negative wire values cost as little as small positive ones).
 //
 // Two bucket layouts:
-//   table mode   (fixed bases, the zkey's SRS): the bases come with the window
-//                shifts 2^(c w) P_i precomputed once (G1Table), so every window
+//   table mode   (fixed bases, the zkey's SRS and its Lagrange form): the bases come with
+//                the window shifts 2^(c w) P_i precomputed once (G1Table), so every window
 //                feeds ONE bucket set per MSM and there is no per-window Horner;
 //                c = 20 -> 13 digits per scalar instead of 16.
 //   window mode  (one-shot bases, nzcb_msm_g1): one bucket set per window, Horner
@@ -16,19 +16,21 @@
 // Several MSMs over the same bases (A/B/C, T1/T2/T3, Wxi/Wxiw) run as one batch of
 // "jobs": one sort, one accumulation launch, one reduction.
 //
-//   1. k_msm_digits<COUNT>   recode, histogram the bucket keys
+//   1. k_msm_digits<COUNT>   recode, histogram the bucket keys (warp-aggregated atomics)
 //   2. scan_excl             bucket offsets (multi-block)
 //   3. k_msm_digits<SCATTER> counting-sort the point references by bucket
-//   4. k_msm_accum           THE hot kernel.  Equal-length segments of the sorted
-//                            list per thread (perfect balance whatever the bucket
-//                            sizes): XYZZ += affine (8M + 2S) along the segment;
-//                            buckets inside a segment are written directly, the
-//                            first / last (possibly shared with the neighbours) go
-//                            to a (key, partial) list
-//      k_seg_level           segmented reduction of that list, level by level
-//   5. k_bred                sum_b (b+1) B_b by chunked running sums, recursively
-//      k_msm_finish          window mode: Horner over the windows
-// Algorithmic work: n * 16 * 10 modmul in step 4.
+//   4. k_msm_accum           THE hot kernel.  Chunks of 64 consecutive entries of the sorted
+//                            list per thread, tiles of 256 chunks drawn from an atomic counter by
+//                            a persistent grid: XYZZ += affine (8M + 2S) along the chunk;
+//                            buckets inside a chunk are written directly, the first / last
+//                            (possibly shared with the neighbours) go to a (key, partial) list
+//      k_seg_join            adds up the short runs of that list (a bucket straddling a boundary)
+//      k_seg_level           segmented reduction of what is left, level by level
+//   5. k_bred                sum_b (b+1) B_b: chunked running sums over all buckets,
+//      k_bred_pair           then one halving per launch
+//      k_msm_horner          window mode: Horner over the windows
+// Latency mode: a ctx may own only a slice of the point range (msm_table_finish exchanges the
+// partial sums).   Algorithmic work: n * 16 * 10 modmul in step 4.
 #include "common.cuh"
 #include <stdlib.h>
 #include <algorithm>

@@ -6,14 +6,15 @@
 // nzcb_circom_b200/circom/builder.py): one instruction per wire, sorted by
 // dependency level.
 //
-// Execution model: one CTA per pass; a level's instructions are spread over the
-// CTA's threads, levels are separated by __syncthreads.  Wires live in HBM in
+// Execution model: one CTA (256 threads) per pass; a level's instructions are spread over the
+// CTA -- long linear combinations one per warp, the rest one per thread from records prefetched
+// into shared memory -- and levels are separated by __syncthreads.  Wires live in HBM in
 // canonical (non-Montgomery) little-endian form, pass-major, so a pass's first
 // nWitness wires ARE the payload of its .wtns file and feed the prover without a
-// copy.  Constants are Montgomery, so const * wire is a single multiply;
-// wire * wire takes two.  IsZero's inverse hint hits a 2 x 1024-entry table for
-// the |x| <= 1024 operands the CBOR selectors produce and
-// falls back to a Fermat inverse otherwise.
+// copy.  Constants are kept in both forms, so const * wire is at most a single multiply
+// (none for bit wires); wire * wire takes two unless both fit 32 bits.  IsZero's inverse hint
+// hits a 2 x 1024-entry table for the |x| <= 1024 operands the CBOR selectors produce
+//  and falls back to a Fermat inverse otherwise.
 #include "common.cuh"
 #include <algorithm>
 #include <cuda_pipeline.h>
