@@ -28,5 +28,5 @@ def nzcp_live_prover(ctx):
     from nzcb_circom_b200.prover import NzcpProver, default_tau
 
     pr = NzcpProver(live=True, tau=default_tau(), ctx=ctx)
-    pr.setup()
+    pr.zkey_bytes = pr.setup(keep_zkey=True)  # kept for the full-size byte comparison against the C oracle
     return pr

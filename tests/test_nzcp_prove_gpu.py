@@ -119,3 +119,20 @@ def test_msm_split_latency_mode_two_ranks_one_gpu(nzcp_live_prover):
     assert results[0] == expect and results[1] == expect
     pr1.zk.close()
     ctx1.close()
+
+
+def test_nzcp_live_proof_bytes_equal_c_oracle_full_size(nzcp_live_prover):
+    """Full size (domain 2^21), same zkey bytes, same pass, same blinders: the GPU proof and the proof of the C port
+    of the oracle (snarkjs' schedule: monomial-basis commitments, T / Tz halves, two inverse transforms -- none of
+    the shortcuts the GPU prover takes) are the same 800 bytes."""
+    from oracle import c_oracle as C
+
+    pr = nzcp_live_prover
+    C.use_all_cores()
+    p = H.synth_pass(33)
+    inp = pr.marshal_passes([(p["toBeSigned"], p["data"])])
+    bl = list(range(11, 20))
+    rc, cproof, cpub = C.fullprove(pr.art.wprog_bytes(), inp, pr.zkey_bytes, bl, 3)
+    assert rc == 0
+    gproof, gpub, st = pr.prove_raw(inp, 1, [bl])[0]
+    assert st == 0 and gproof == cproof and [int(x) for x in gpub] == list(cpub)
