@@ -140,7 +140,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
-    ap.add_argument("--batch", type=int, default=16, help="passes per GPU per step")
+    ap.add_argument("--batch", type=int, default=32, help="passes per GPU per step")
     ap.add_argument("--impl", default="nzcb")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

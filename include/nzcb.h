@@ -78,6 +78,9 @@ int32_t nzcb_ctx_set_msm_split(nzcb_ctx* ctx, int32_t rank, int32_t world,
 int32_t nzcb_microbench(nzcb_ctx* ctx, int32_t kind, uint32_t iters, uint32_t blocks_per_sm, double* ops_per_s);
 /* mixed-addition (XYZZ += affine, the body of the MSM accumulation) loop variants; result in additions/s */
 int32_t nzcb_microbench_madd(nzcb_ctx* ctx, int32_t variant, uint32_t iters, uint32_t log_table, double* madds_per_s);
+/* store -> barrier -> dependent load round trip of one CTA through global (kind 0) or shared (kind 1) memory: the
+ * floor of one level of the witness interpreter; result in ns per level */
+int32_t nzcb_microbench_level(nzcb_ctx* ctx, int32_t kind, uint32_t iters, double* ns_per_level);
 /* device self-test: carry-chain multiply vs portable CIOS on n random operand pairs x 16 */
 int32_t nzcb_selftest_mul(nzcb_ctx* ctx, uint32_t n, uint64_t* mismatches);
 

@@ -47,6 +47,7 @@ SIGNATURES = {
     "nzcb_ctx_set_msm_split": (_i32, [_vp, _i32, _i32, _vp, _vp]),
     "nzcb_microbench": (_i32, [_vp, _i32, _u32, _u32, ctypes.POINTER(ctypes.c_double)]),
     "nzcb_microbench_madd": (_i32, [_vp, _i32, _u32, _u32, ctypes.POINTER(ctypes.c_double)]),
+    "nzcb_microbench_level": (_i32, [_vp, _i32, _u32, ctypes.POINTER(ctypes.c_double)]),
     "nzcb_selftest_mul": (_i32, [_vp, _u32, ctypes.POINTER(ctypes.c_uint64)]),
     "nzcb_ntt_fr": (_i32, [_vp, _vp, _u32, _i32]),
     "nzcb_msm_g1": (_i32, [_vp, _vp, _vp, _sz, _vp]),
@@ -167,6 +168,11 @@ class Context:
     def microbench_madd(self, variant, iters=2000, log_table=10):
         v = ctypes.c_double()
         self.check(self.lib.nzcb_microbench_madd(self.h, variant, iters, log_table, ctypes.byref(v)))
+        return v.value
+
+    def microbench_level(self, kind, iters=20000):
+        v = ctypes.c_double()
+        self.check(self.lib.nzcb_microbench_level(self.h, kind, iters, ctypes.byref(v)))
         return v.value
 
     def profile(self, enable=True):

@@ -247,3 +247,52 @@ extern "C" int32_t nzcb_microbench_madd(nzcb_ctx* ctx, int32_t variant, uint32_t
     *madds_per_s = (double)iters * grid * threads / (ctx->last_ms * 1e-3);
     return 0;
 }
+
+
+// ---- level round trip of the witness interpreter: store -> barrier -> dependent load, through global memory
+// (kind 0) or shared memory (kind 1); one CTA of 256 threads, `iters` levels.  Result: nanoseconds per level.
+__global__ void __launch_bounds__(256) k_level_roundtrip(uint32_t* __restrict__ buf, uint32_t iters, int kind, uint32_t* out) {
+    __shared__ uint32_t sm[256 * 8];
+    const uint32_t t = threadIdx.x;
+    uint32_t v[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) v[k] = t + k;
+    for (uint32_t i = 0; i < iters; i++) {
+        const uint32_t dst = ((i * 256u + t) & 0xffffu) * 8, src = ((i * 256u + ((t + 37u) & 255u)) & 0xffffu) * 8;
+        if (kind == 0) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) buf[dst + k] = v[k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; k++) sm[k * 256 + t] = v[k];
+        }
+        __syncthreads();
+        if (kind == 0) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[k] += buf[src + k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[k] += sm[k * 256 + ((t + 37u) & 255u)];
+        }
+        __syncthreads();
+    }
+    uint32_t x = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) x ^= v[k];
+    out[t] = x;
+}
+
+extern "C" int32_t nzcb_microbench_level(nzcb_ctx* ctx, int32_t kind, uint32_t iters, double* ns_per_level) {
+    if (!ctx || !ns_per_level || kind < 0 || kind > 1) return NZCB_E_INVALID;
+    uint32_t* buf = (uint32_t*)ctx->scratch_get("level_buf", (size_t)65536 * 32 + 4096);
+    if (!buf) return ctx->fail(NZCB_E_NOMEM, "microbench: out of memory");
+    for (int rep = 0; rep < 2; rep++) {
+        NZ_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+        NZ_LAUNCH(ctx, k_level_roundtrip, 1, 256, 0, buf, iters, kind, buf + 65536 * 8);
+        NZ_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+        NZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1);
+    *ns_per_level = ctx->last_ms * 1e6 / iters;
+    return 0;
+}

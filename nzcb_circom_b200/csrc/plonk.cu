@@ -965,7 +965,7 @@ uint32_t circuit_n_in(const nzcb_circuit* c);
 namespace {
 
 int lane_count(size_t B) {
-    int L = 3;
+    int L = 4;
     const char* env = getenv("NZCB_LANES");
     if (env && atoi(env) >= 1 && atoi(env) <= 8) L = atoi(env);
     if ((size_t)L > B) L = (int)B;
