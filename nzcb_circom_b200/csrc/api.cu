@@ -84,6 +84,8 @@ extern "C" void nzcb_ctx_free(nzcb_ctx* ctx) {
         cudaEventDestroy(e.first);
         cudaEventDestroy(e.second);
     }
+    if (ctx->side) cudaStreamDestroy(ctx->side);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);

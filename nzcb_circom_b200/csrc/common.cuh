@@ -33,6 +33,8 @@ struct nzcb_ctx {
     int (*split_allgather)(void* user, const void* send, void* recv, size_t bytes) = nullptr;
     void* split_user = nullptr;
     cudaStream_t stream = nullptr;
+    cudaStream_t side = nullptr;         // second stream of this ctx / lane: commitments overlap the transforms of a round
+    cudaEvent_t ev_fork = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float last_ms = 0.f;
     uint64_t launches = 0;

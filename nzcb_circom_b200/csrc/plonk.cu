@@ -621,8 +621,8 @@ struct Tracer {
     }
 };
 
-// evaluations -> (blinded coefficient polynomial, its 4n evaluations on the coset)   [role of snarkjs to4T]
-int to4t(nzcb_ctx* ctx, const nzcb_zkey* zk, const Fr* d_evals, Fr* d_pol, Fr* d_ext, const Fr* pz, int k) {
+// evaluations -> blinded coefficient polynomial   [first half of the role of snarkjs to4T]
+int to_coef(nzcb_ctx* ctx, const nzcb_zkey* zk, const Fr* d_evals, Fr* d_pol, const Fr* pz, int k) {
     const size_t n = zk->n;
     NZ_CUDA(ctx, cudaMemcpyAsync(d_pol, d_evals, n * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->stream));
     NZ_TRY(ntt_dev(ctx, d_pol, zk->power, true));
@@ -630,11 +630,33 @@ int to4t(nzcb_ctx* ctx, const nzcb_zkey* zk, const Fr* d_evals, Fr* d_pol, Fr* d
     bl.k = k;
     for (int i = 0; i < 3; i++) bl.pz[i] = i < k ? pz[i] : Fr::zero();
     NZ_LAUNCH(ctx, k_blind, 1, 32, 0, d_pol, n, bl);
-    // the blinded polynomial on the coset g * H_4n (round 3)
-    NZ_LAUNCH(ctx, k_scale_pad, div_up(4 * n, 256), 256, 0, d_pol, n + (size_t)k, zk->d_gpow, d_ext, 4 * n);
-    NZ_TRY(ntt_dev(ctx, d_ext, zk->power + 2, false));
     return 0;
 }
+// blinded polynomial (n + k coefficients) -> its 4n evaluations on the coset g * H_4n (round 3)
+int to_coset(nzcb_ctx* ctx, const nzcb_zkey* zk, const Fr* d_pol, Fr* d_ext, int k) {
+    const size_t n = zk->n;
+    NZ_LAUNCH(ctx, k_scale_pad, div_up(4 * n, 256), 256, 0, d_pol, n + (size_t)k, zk->d_gpow, d_ext, 4 * n);
+    return ntt_dev(ctx, d_ext, zk->power + 2, false);
+}
+
+// While alive, everything enqueued through the ctx goes to its side stream, which first waits for what the main stream
+// holds so far (fork = true) -- the commitments of a round run beside its transforms.  The destructor switches back;
+// whoever needs the results synchronises the side stream (msm_table_finish does).
+struct SideStream {
+    nzcb_ctx* ctx;
+    cudaStream_t main;
+    bool ok = false;
+    SideStream(nzcb_ctx* c, bool fork) : ctx(c), main(c->stream) {
+        if (!ctx->side && cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking) != cudaSuccess) return;
+        if (!ctx->ev_fork && cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess) return;
+        if (fork && (cudaEventRecord(ctx->ev_fork, main) != cudaSuccess ||
+                     cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0) != cudaSuccess))
+            return;
+        ctx->stream = ctx->side;
+        ok = true;
+    }
+    ~SideStream() { ctx->stream = main; }
+};
 
 // d_w_le: device, n_w canonical little-endian witness values (NOT yet Montgomery); may alias b.w_le.
 // h_pub_le: host copy of w[1..nPublic] (canonical LE) for the transcript.
@@ -709,23 +731,33 @@ int prove_core(nzcb_ctx* ctx, const nzcb_zkey* zk, const Fr* d_w_le, const uint8
     NZ_LAUNCH(ctx, k_gather, div_up(n, 256), 256, 0, zk->d_map[0], b.W, zk->n_vars, zk->n_cons, n, b.A);
     NZ_LAUNCH(ctx, k_gather, div_up(n, 256), 256, 0, zk->d_map[1], b.W, zk->n_vars, zk->n_cons, n, b.B);
     NZ_LAUNCH(ctx, k_gather, div_up(n, 256), 256, 0, zk->d_map[2], b.W, zk->n_vars, zk->n_cons, n, b.C);
-    {
-        const Fr pa[2] = {bl[2], bl[1]}, pb[2] = {bl[4], bl[3]}, pc[2] = {bl[6], bl[5]};
-        NZ_TRY(to4t(ctx, zk, b.A, b.pol_a, b.A4, pa, 2));
-        NZ_TRY(to4t(ctx, zk, b.B, b.pol_b, b.B4, pb, 2));
-        NZ_TRY(to4t(ctx, zk, b.C, b.pol_c, b.C4, pc, 2));
-    }
-    tr_.mark("r1 ntt");
     G1Affine cA, cB, cC, cZ, cT1, cT2, cT3, cWxi, cWxiw;
-    {   // Lagrange basis: the scalars are the wire values (mostly 0 / +-1 / bytes) plus four blinding terms
+    {   // Lagrange basis: the scalars are the wire values (mostly 0 / +-1 / bytes) plus four blinding terms.  The
+        // commitments only need the evaluations, so they run on the side stream beside the round's transforms.
         NZ_LAUNCH(ctx, k_blind_scalars, 1, 32, 0, b.A, (size_t)n, bl[2], bl[1]);
         NZ_LAUNCH(ctx, k_blind_scalars, 1, 32, 0, b.B, (size_t)n, bl[4], bl[3]);
         NZ_LAUNCH(ctx, k_blind_scalars, 1, 32, 0, b.C, (size_t)n, bl[6], bl[5]);
         const uint32_t* sc[3] = {(const uint32_t*)b.A, (const uint32_t*)b.B, (const uint32_t*)b.C};
         const size_t sn[3] = {(size_t)n + 4, (size_t)n + 4, (size_t)n + 4};
+        {
+            SideStream side(ctx, true);
+            if (!side.ok) return ctx->fail(NZCB_E_CUDA, "prove: cannot set up the side stream");
+            NZ_TRY(msm_table_dev(ctx, zk->tab_lag, sc, sn, 3, true, b.pts));
+        }
+        const Fr pa[2] = {bl[2], bl[1]}, pb[2] = {bl[4], bl[3]}, pc[2] = {bl[6], bl[5]};
+        NZ_TRY(to_coef(ctx, zk, b.A, b.pol_a, pa, 2));
+        NZ_TRY(to_coset(ctx, zk, b.pol_a, b.A4, 2));
+        NZ_TRY(to_coef(ctx, zk, b.B, b.pol_b, pb, 2));
+        NZ_TRY(to_coset(ctx, zk, b.pol_b, b.B4, 2));
+        NZ_TRY(to_coef(ctx, zk, b.C, b.pol_c, pc, 2));
+        NZ_TRY(to_coset(ctx, zk, b.pol_c, b.C4, 2));
+        tr_.mark("r1 ntt");
         G1Affine r[3];
-        NZ_TRY(msm_table_dev(ctx, zk->tab_lag, sc, sn, 3, true, b.pts));
-        NZ_TRY(msm_table_finish(ctx, b.pts, r, 3));
+        {
+            SideStream side(ctx, false);
+            if (!side.ok) return ctx->fail(NZCB_E_CUDA, "prove: cannot set up the side stream");
+            NZ_TRY(msm_table_finish(ctx, b.pts, r, 3));
+        }
         cA = r[0]; cB = r[1]; cC = r[2];
     }
     g1_to_be(cA, out->A);
@@ -782,16 +814,23 @@ int prove_core(nzcb_ctx* ctx, const nzcb_zkey* zk, const Fr* d_w_le, const uint8
         if (total != Fr::one()) return ctx->fail(NZCB_E_COPY, "Copy constraints does not match");
     }
     tr_.mark("r2 grandprod");
-    {
+    {   // the commitment needs the coefficients, not the coset evaluations: it starts as soon as they exist
         const Fr pz[3] = {bl[9], bl[8], bl[7]};
-        NZ_TRY(to4t(ctx, zk, b.den, b.pol_z, b.Z4, pz, 3));
-    }
-    tr_.mark("r2 ntt");
-    {
+        NZ_TRY(to_coef(ctx, zk, b.den, b.pol_z, pz, 3));
         const uint32_t* sc[1] = {(const uint32_t*)b.pol_z};
         const size_t sn[1] = {(size_t)n + 3};
-        NZ_TRY(msm_table_dev(ctx, zk->tab, sc, sn, 1, true, b.pts));
-        NZ_TRY(msm_table_finish(ctx, b.pts, &cZ, 1));
+        {
+            SideStream side(ctx, true);
+            if (!side.ok) return ctx->fail(NZCB_E_CUDA, "prove: cannot set up the side stream");
+            NZ_TRY(msm_table_dev(ctx, zk->tab, sc, sn, 1, true, b.pts));
+        }
+        NZ_TRY(to_coset(ctx, zk, b.pol_z, b.Z4, 3));
+        tr_.mark("r2 ntt");
+        {
+            SideStream side(ctx, false);
+            if (!side.ok) return ctx->fail(NZCB_E_CUDA, "prove: cannot set up the side stream");
+            NZ_TRY(msm_table_finish(ctx, b.pts, &cZ, 1));
+        }
     }
     g1_to_be(cZ, out->Z);
 
