@@ -219,6 +219,10 @@ class Circuit:
         self.constraints.append((_terms(q.a), _terms(q.b), _terms(LC({w: 1}) - q.c)))
         return LC({w: 1})
 
+    def chain(self):
+        """Running sum  s_i <== a_i * b_i + s_(i-1)  (s_(-1) = 0): see MulSumChain."""
+        return MulSumChain(self)
+
     def wire(self, x):
         """force a real signal equal to x (s <== x)"""
         if isinstance(x, Quad):
@@ -299,6 +303,75 @@ class Circuit:
         return Compiled(self)
 
 
+class MulSumChain:
+    """s_i <== a_i * b_i + s_(i-1), the running sum of quinSelector.circom:37.  step() allocates the signal and the
+    constraint of one step exactly where a plain ``quad`` would (same wire numbering, same R1CS); only the witness
+    PROGRAM differs: finish() emits products -> block totals -> block prefixes -> prefix sums, four dependency levels
+    whatever the length, instead of one level per step (351 for GetV(351), the bulk of the circuit's critical path).
+    The intermediate values live in program temps, which are not part of the witness."""
+
+    def __init__(self, c):
+        self.c = c
+        self.steps = []      # (wire, a, b)
+        self.acc = LC()
+        self.plain = False   # a degenerate (linear) step was met: fall back to one instruction per step
+
+    def step(self, a, b):
+        c = self.c
+        a, b = LC.of(a), LC.of(b)
+        if self.plain or a.is_const() or b.is_const():
+            if not self.plain:
+                self._emit_plain()
+                self.plain = True
+            self.acc = c.quad(a * b + self.acc)
+            return self.acc
+        w = c._new_wire()
+        c.constraints.append((_terms(a), _terms(b), _terms(LC({w: 1}) - self.acc)))
+        self.steps.append((w, a, b))
+        self.acc = LC({w: 1})
+        return self.acc
+
+    def _emit_plain(self):
+        prev = LC()
+        for w, a, b in self.steps:
+            self.c.prog.append((OP_MUL, w, a, b, prev))
+            prev = LC({w: 1})
+        self.steps = []
+
+    def finish(self):
+        c = self.c
+        n = len(self.steps)
+        if self.plain or n <= 8:
+            self._emit_plain()
+            return self.acc
+        prods = []
+        for _, a, b in self.steps:
+            t = c._new_temp()
+            c.prog.append((OP_MUL, t, a, b, LC()))
+            prods.append(t)
+        blk = 1
+        while blk * blk < n:
+            blk += 1
+        totals = []      # block totals
+        for k in range(0, n, blk):
+            t = c._new_temp()
+            c.prog.append((OP_LIN, t, LC({p: 1 for p in prods[k:k + blk]})))
+            totals.append(t)
+        prefixes = [None]  # prefixes[k] = sum of the totals of blocks < k
+        for k in range(1, len(totals)):
+            t = c._new_temp()
+            c.prog.append((OP_LIN, t, LC({x: 1 for x in totals[:k]})))
+            prefixes.append(t)
+        for i, (w, _, _) in enumerate(self.steps):
+            k = i // blk
+            terms = {p: 1 for p in prods[k * blk:i + 1]}
+            if prefixes[k] is not None:
+                terms[prefixes[k]] = 1
+            c.prog.append((OP_LIN, w, LC(terms)))
+        self.steps = []
+        return self.acc
+
+
 class Compiled:
     """Finalised circuit: R1CS + witness program with temps remapped and levels computed."""
 
@@ -332,9 +405,10 @@ class Compiled:
                 prog.append((op, dst, lc))
             elif op == OP_MUL:
                 a, b, cc = rlc(ins[2]), rlc(ins[3]), rlc(ins[4])
+                dst = rid(ins[1])
                 l = 1 + max((level[w] for lc in (a, b, cc) for w in lc.t), default=0)
-                level[ins[1]] = l
-                prog.append((op, ins[1], a, b, cc))
+                level[dst] = l
+                prog.append((op, dst, a, b, cc))
             elif op == OP_BITS:
                 src = rid(ins[2])
                 l = 1 + level[src]

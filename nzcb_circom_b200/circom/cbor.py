@@ -24,11 +24,11 @@ def quin_selector(c: Circuit, ins, index):
         bits = log2(choices) + 1
         lt = less_than(c, bits, index, choices)          # :19-24
         c.assert_eq(lt, 1)
-    sums = LC()
+    chain = c.chain()                                     # sums[i] <== eqs[i] * in[i] + sums[i-1]
     for i in range(choices):
         eq = is_zero(c, i - index)                        # :32-33
-        sums = c.quad(eq * LC.of(ins[i]) + sums)          # :37
-    return sums                                           # :41  (0 when choices == 0)
+        chain.step(eq, ins[i])                            # :37
+    return chain.finish()                                 # :41  (0 when choices == 0)
 
 
 def get_type(c, v):

@@ -136,3 +136,37 @@ def test_nzcp_live_proof_bytes_equal_c_oracle_full_size(nzcp_live_prover):
     assert rc == 0
     gproof, gpub, st = pr.prove_raw(inp, 1, [bl])[0]
     assert st == 0 and gproof == cproof and [int(x) for x in gpub] == list(cpub)
+
+
+def test_witness_batch_65536_passes(ctx):
+    """BASELINE.json configs[3] at full size: 65,536 nzcp_live passes through the batched witness program (8 calls of
+    8,192 sharing one marshalled buffer).  Size-independent property: exactly the corrupted passes are rejected
+    ("Assert Failed"), every other pass is accepted -- a failed pass never fails its batch."""
+    import ctypes
+
+    from nzcb_circom_b200.circom_tester import wasm_tester
+
+    cir = wasm_tester("nzcp_live", ctx)
+    art = cir.compiled
+    distinct = []
+    for s in range(32):
+        p = H.synth_pass(500 + s)
+        vals = art.flatten_input(H.nzcp_input(p["toBeSigned"], 351, p["data"]))
+        distinct.append(b"".join(int(v).to_bytes(32, "little") for v in vals))
+    bad = bytearray(distinct[0])
+    bad[0:32] = (2).to_bytes(32, "little")  # first ToBeSigned bit is not boolean (nzcptpl.circom:493-496)
+    B = 8192
+    rows = [distinct[i % 32] for i in range(B)]
+    bad_at = set(range(5, B, 1021))
+    for i in bad_at:
+        rows[i] = bytes(bad)
+    buf = b"".join(rows)
+    status = (ctypes.c_int32 * B)()
+    h = cir._handle(ctx)
+    total_ms = 0.0
+    for _ in range(8):
+        ctx.check(ctx.lib.nzcb_witness_batch(ctx.h, h, buf, B, None, status))
+        total_ms += ctx.last_device_ms
+        st = list(status)
+        assert all((st[i] == -6) == (i in bad_at) and st[i] in (0, -6) for i in range(B))
+    print(f"65,536 passes in {total_ms:.0f} ms of device time ({65536 / total_ms * 1e3:.0f} passes/s)")
