@@ -20,7 +20,7 @@ import struct
 
 R = 0x30644e72e131a029b85045b68181585d2833e84879b9709143e1f593f0000001
 
-OP_LIN, OP_MUL, OP_BITS, OP_INV, OP_ASSERT = 1, 2, 3, 4, 5
+OP_LIN, OP_MUL, OP_BITS, OP_INV, OP_ASSERT, OP_BITSLC = 1, 2, 3, 4, 5, 6
 
 
 class LC:
@@ -264,10 +264,14 @@ class Circuit:
     def hint_bits(self, x, n):
         """out[i] <-- (x >> i) & 1, i < n   (no constraints)"""
         self._io_closed = True
-        src = self._src(x)
+        x = LC.of(x)
         first = self.n_wires
         self.n_wires += n
-        self.prog.append((OP_BITS, first, src, n))
+        w = x.single_wire()
+        if w is not None:
+            self.prog.append((OP_BITS, first, w, n))
+        else:  # the sum is evaluated and decomposed by ONE instruction: no temp, no extra dependency level
+            self.prog.append((OP_BITSLC, first, n, x))
         return [LC({first + i: 1}) for i in range(n)]
 
     def hint_inv(self, x):
@@ -420,6 +424,12 @@ class Compiled:
                 l = 1 + level[src]
                 level[ins[1]] = l
                 prog.append((op, ins[1], src))
+            elif op == OP_BITSLC:
+                lc = rlc(ins[3])
+                l = 1 + max((level[w] for w in lc.t), default=0)
+                for i in range(ins[2]):
+                    level[ins[1] + i] = l
+                prog.append((op, ins[1], ins[2], lc))
             else:
                 a, b, cc = rlc(ins[1]), rlc(ins[2]), rlc(ins[3])
                 l = 1 + max((level[w] for lc in (a, b, cc) for w in lc.t), default=0)
@@ -471,6 +481,7 @@ class Compiled:
            BITS   op, dst0, src, n
            INV    op, dst, src
            ASSERT op, <lc a>, <lc b>, <lc c>
+           BITSLC op, dst0, n, <lc>          (bits of the value of an LC)
            <lc> = n_terms, const_idx (0xffffffff = no constant), then n_terms x (wire, coef_idx)"""
         consts = {1: 0, R - 1: 1}
         clist = [1, R - 1]
@@ -506,6 +517,9 @@ class Compiled:
                 code.extend((ins[1], ins[2], ins[3]))
             elif op == OP_INV:
                 code.extend((ins[1], ins[2]))
+            elif op == OP_BITSLC:
+                code.extend((ins[1], ins[2]))
+                emit_lc(ins[3])
             else:
                 emit_lc(ins[1]); emit_lc(ins[2]); emit_lc(ins[3])
         lstart = [0] * (self.n_levels + 1)

@@ -21,7 +21,7 @@
 
 using namespace nzcb;
 
-enum { OP_LIN = 1, OP_MUL = 2, OP_BITS = 3, OP_INV = 4, OP_ASSERT = 5 };
+enum { OP_LIN = 1, OP_MUL = 2, OP_BITS = 3, OP_INV = 4, OP_ASSERT = 5, OP_BITSLC = 6 };
 constexpr uint32_t NZ_INV_TAB = 1024;
 constexpr uint32_t NZ_LONG_LC = 24;  // an LC (or bit decomposition) longer than this is evaluated by a whole warp
 
@@ -197,6 +197,15 @@ __device__ __forceinline__ bool exec_instr(const ProgView& pv, const RD& rd, Fr*
             bit.v[0] = k < 256 ? (v.v[k >> 5] >> (k & 31)) & 1u : 0u;
             W[dst + k] = bit;
         }
+    } else if (op == OP_BITSLC) {  // bits of the value of an LC: the sum and its decomposition in one instruction
+        const uint32_t dst = rd(p + 1), n = rd(p + 2);
+        p += 3;
+        const Fr v = LC(p);  // warp mode: every lane holds the value
+        for (uint32_t k = WARP ? lane : 0; k < n; k += WARP ? 32 : 1) {
+            Fr bit = Fr::zero();
+            bit.v[0] = k < 256 ? (v.v[k >> 5] >> (k & 31)) & 1u : 0u;
+            W[dst + k] = bit;
+        }
     } else if (op == OP_INV) {
         if (commit) W[rd(p + 1)] = inv_or_zero(pv, W[rd(p + 2)]);
     } else {  // OP_ASSERT
@@ -303,7 +312,7 @@ __global__ void __launch_bounds__(WIT_THREADS) k_witness(ProgView pv, const Fr* 
                 const SmemCode scode{reinterpret_cast<const uint32_t*>(slot(buf, 0))};
                 const uint32_t w0 = scode(0), op = w0 & 0xffu;
                 if (w0 & REC_LONG) failed |= exec_instr<false>(pv, gcode, W, scode(1), lane);
-                else if (op == OP_BITS || op == OP_INV) failed |= exec_instr<false>(pv, scode, W, 0, lane);
+                else if (op == OP_BITS || op == OP_INV || op == OP_BITSLC) failed |= exec_instr<false>(pv, scode, W, 0, lane);
                 else failed |= exec_short(pv, scode, W, op);
                 for (i += WIT_THREADS; i < hi; i += WIT_THREADS) failed |= exec_instr<false>(pv, gcode, W, pv.ioff[i], lane);
             }
@@ -420,6 +429,12 @@ extern "C" int32_t nzcb_circuit_load(nzcb_ctx* ctx, const uint8_t* data, size_t 
             } else if (op == OP_BITS) {
                 ok = p + 4 <= c->n_code && code[p + 2] < c->n_total && (uint64_t)code[p + 1] + code[p + 3] <= c->n_total;
                 if (ok) cur_weight = code[p + 3];
+            } else if (op == OP_BITSLC) {
+                ok = p + 3 <= c->n_code && (uint64_t)code[p + 1] + code[p + 2] <= c->n_total;
+                const uint32_t n_bits = ok ? code[p + 2] : 0;
+                p += 3;
+                ok = ok && lc_ok(p);
+                if (ok) cur_weight = std::max(cur_weight, n_bits);
             } else if (op == OP_INV) {
                 ok = p + 3 <= c->n_code && code[p + 1] < c->n_total && code[p + 2] < c->n_total;
             } else if (op == OP_ASSERT) {
@@ -453,6 +468,7 @@ extern "C" int32_t nzcb_circuit_load(nzcb_ctx* ctx, const uint8_t* data, size_t 
             uint32_t len;
             if (op == OP_BITS) len = 4;
             else if (op == OP_INV) len = 3;
+            else if (op == OP_BITSLC) len = 3 + 2 + 2 * code[p + 3];
             else {
                 uint32_t q = p + (op == OP_ASSERT ? 1 : 2);
                 for (uint32_t j = 0; j < (op == OP_LIN ? 1u : 3u); j++) q += 2 + 2 * code[q];

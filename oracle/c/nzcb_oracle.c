@@ -301,7 +301,7 @@ static void g1_to_be(uint8_t out[64], const g1a* p) {
 }
 
 /* ---- witness program interpreter (oracle/witness_vm.py) ---- */
-enum { OP_LIN = 1, OP_MUL = 2, OP_BITS = 3, OP_INV = 4, OP_ASSERT = 5 };
+enum { OP_LIN = 1, OP_MUL = 2, OP_BITS = 3, OP_INV = 4, OP_ASSERT = 5, OP_BITSLC = 6 };
 static fe eval_lc(const uint32_t* code, uint32_t* p, const fe* consts_m, const fe* W) {
     const uint32_t n = code[*p], ci = code[*p + 1];
     *p += 2;
@@ -345,6 +345,11 @@ int oracle_witness(const uint8_t* wprog, size_t len, const uint8_t* inputs_le, u
         } else if (op == OP_BITS) {
             const uint32_t d = code[p + 1], src = code[p + 2], n = code[p + 3];
             const fe v = W[src];
+            for (uint32_t k = 0; k < n; k++) { f_zero(&W[d + k]); W[d + k].v[0] = k < 256 ? (v.v[k >> 6] >> (k & 63)) & 1 : 0; }
+        } else if (op == OP_BITSLC) {
+            const uint32_t d = code[p + 1], n = code[p + 2];
+            p += 3;
+            const fe v = eval_lc(code, &p, cm, W);
             for (uint32_t k = 0; k < n; k++) { f_zero(&W[d + k]); W[d + k].v[0] = k < 256 ? (v.v[k >> 6] >> (k & 63)) & 1 : 0; }
         } else if (op == OP_INV) {
             fe v = W[code[p + 2]], m;

@@ -12,7 +12,7 @@ import struct
 from .binfile import read_r1cs
 from .bn254 import R_MOD as R
 
-OP_LIN, OP_MUL, OP_BITS, OP_INV, OP_ASSERT = 1, 2, 3, 4, 5
+OP_LIN, OP_MUL, OP_BITS, OP_INV, OP_ASSERT, OP_BITSLC = 1, 2, 3, 4, 5, 6
 
 
 class AssertFailed(Exception):
@@ -74,6 +74,11 @@ def run(prog: Program, inputs, check=True):
         elif op == OP_INV:
             v = w[code[off + 2]]
             w[code[off + 1]] = pow(v, R - 2, R) if v else 0
+        elif op == OP_BITSLC:
+            dst, n = code[off + 1], code[off + 2]
+            v, _ = lc(off + 3)
+            for i in range(n):
+                w[dst + i] = (v >> i) & 1
         elif op == OP_ASSERT:
             a, p = lc(off + 1)
             b, p = lc(p)
