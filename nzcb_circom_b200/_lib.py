@@ -4,7 +4,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libnzcb.so")
+LIB_PATH = os.environ.get("NZCB_LIB_PATH") or os.path.join(HERE, "libnzcb.so")  # override: A/B builds of the library
 
 NZCB_OK = 0
 NZCB_E_INVALID = -1

@@ -70,7 +70,7 @@ __device__ __forceinline__ void lc_term(const ProgView& pv, Fr& acc, uint32_t c,
     else acc = acc + wit_mul(pv.consts[c], v);  // Montgomery const x canonical wire = canonical
 }
 
-constexpr uint32_t WIT_THREADS = 256;
+constexpr uint32_t WIT_THREADS = 384;
 constexpr uint32_t REC_WORDS = 32;
 constexpr uint32_t REC_LONG = 0x100u;  // flag on word 0: the encoding does not fit a record, word 1 = its code offset
 
