@@ -178,6 +178,33 @@ int32_t nzcb_plonk_fullprove_batch_dev(nzcb_ctx* ctx, const nzcb_circuit* c, con
                                        const void* d_inputs_le, size_t B, const uint8_t* blinders_le, nzcb_proof* out,
                                        uint8_t* public_le, int32_t* status);
 
+/* ---- pass ingest: the host helpers the reference's tests run before calculateWitness ---------------------
+ * getCOSE + encodeToBeSigned (/root/reference/test/helpers/nzcp.js:9-24 base32ToBytes, :58-105 decodeCBORStream,
+ * :141-172 decodeBytes / decodeCOSE, :180-206 encodeToBeSigned) and the input object of test/nzcp.js:36-41
+ * (fitBytes, bufferToBitArray, evmRearrangeBytes: test/helpers/utils.js:49,2,87) for B passes on the device.
+ * uris: the pass URIs ("NZCP:/1/<base32>", ASCII) back to back, pass i = uris[uri_off[i] .. uri_off[i+1]); the
+ * first 8 characters are skipped unchecked, as decodeBytes does.  data20: B x 20 pass-through bytes (origData of
+ * test/nzcp.js:36) or NULL = zeros.  max_len: 314 (nzcp_example) / 351 (nzcp_live), at most 1024.
+ * tbs_out (may be NULL): B x max_len = fitBytes(ToBeSigned, max_len); tbs_len (may be NULL): the TRUE lengths;
+ * inputs_le (may be NULL): B x (8 max_len + 161) x 32 B LE -- the main inputs in declaration order, what
+ * nzcb_witness_batch / nzcb_plonk_fullprove_batch take.  status[i] = 0 or NZCB_E_INVALID ("invalid data": the JS
+ * helpers throw); a rejected pass yields zeros, tbs_len 0 and toBeSignedLen = 0xFFFF in its inputs (which every
+ * circuit rejects) and never fails the batch.  URIs longer than 4104 characters are rejected. */
+int32_t nzcb_pass_ingest_batch(nzcb_ctx* ctx, const uint8_t* uris, const uint32_t* uri_off, size_t B,
+                               const uint8_t* data20, uint32_t max_len, uint8_t* tbs_out, uint32_t* tbs_len,
+                               uint8_t* inputs_le, int32_t* status);
+/* the same with the marshalled inputs left in HBM (d_inputs_le from nzcb_dev_alloc, B x (8 max_len + 161) x 32 B),
+ * ready for nzcb_plonk_fullprove_batch_dev */
+int32_t nzcb_pass_ingest_batch_dev(nzcb_ctx* ctx, const uint8_t* uris, const uint32_t* uri_off, size_t B,
+                                   const uint8_t* data20, uint32_t max_len, void* d_inputs_le, int32_t* status);
+/* pass URIs -> proofs: ingest, witness program and prover fused on the device; ~0.6 KB per pass cross PCIe
+ * instead of the 95 KB of marshalled inputs.  status[i] = 0, NZCB_E_INVALID (undecodable pass), NZCB_E_ASSERT
+ * (rejected by the circuit) or a prover error. */
+int32_t nzcb_plonk_fullprove_uri_batch(nzcb_ctx* ctx, const nzcb_circuit* c, const nzcb_zkey* zk, const uint8_t* uris,
+                                       const uint32_t* uri_off, size_t B, const uint8_t* data20, uint32_t max_len,
+                                       const uint8_t* blinders_le /* B x 9 x 32 or NULL */, nzcb_proof* out,
+                                       uint8_t* public_le /* B x nPublic x 32 */, int32_t* status /* B */);
+
 /* CUDA-event timing of the dominant kernel (MSM bucket accumulation) on the ctx stream.
  * nzcb_profile(ctx, 1) starts collecting; nzcb_profile_read returns launches, summed device ms and the
  * algorithmic modmul count of those launches (160 per MSM point) and resets. */

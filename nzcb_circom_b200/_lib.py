@@ -72,6 +72,9 @@ SIGNATURES = {
     "nzcb_witness_batch": (_i32, [_vp, _vp, _vp, _sz, _vp, _vp]),
     "nzcb_plonk_fullprove_batch": (_i32, [_vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp]),
     "nzcb_plonk_fullprove_batch_dev": (_i32, [_vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp]),
+    "nzcb_pass_ingest_batch": (_i32, [_vp, _vp, _vp, _sz, _vp, _u32, _vp, _vp, _vp, _vp]),
+    "nzcb_pass_ingest_batch_dev": (_i32, [_vp, _vp, _vp, _sz, _vp, _u32, _vp, _vp]),
+    "nzcb_plonk_fullprove_uri_batch": (_i32, [_vp, _vp, _vp, _vp, _vp, _sz, _vp, _u32, _vp, _vp, _vp, _vp]),
     "nzcb_g1_table_create": (_i32, [_vp, _vp, _sz, ctypes.POINTER(_vp)]),
     "nzcb_g1_table_free": (None, [_vp]),
     "nzcb_msm_g1_table": (_i32, [_vp, _vp, _vp, _sz, _vp]),

@@ -108,3 +108,9 @@ class NzcpProver(CircuitProver):
 
     def prove_passes(self, passes, blinders_list=None):
         return self.prove_raw(self.marshal_passes(passes), len(passes), blinders_list)
+
+    def prove_uris(self, passURIs, datas=None, blinders_list=None):
+        """pass URIs ("NZCP:/1/...") -> proofs, ingest on the device (nzcb_plonk_fullprove_uri_batch)"""
+        from .pass_ingest import fullProveURIs
+
+        return fullProveURIs(passURIs, self.max_len, self.tester, self.zk, datas, blinders_list, self.ctx)

@@ -46,3 +46,25 @@ int fc_g1_op(int op, const uint8_t* a, const uint8_t* b, uint64_t k, uint8_t* ou
 
 #include "../../nzcb_circom_b200/csrc/keccak.h"
 extern "C" void fc_keccak256(const uint8_t* data, size_t len, uint8_t* out) { nzcb::keccak256(data, len, out); }
+
+// ---- pass ingest (csrc/ingest.cuh): the kernel's per-pass steps, run serially ----
+#include "../../nzcb_circom_b200/csrc/ingest.cuh"
+// uri: the whole pass URI; inputs_out: (8 maxLen + 161) u32 values; returns the per-pass status (0 / -1)
+extern "C" int fc_ingest(const uint8_t* uri, uint32_t total, const uint8_t* data20, uint32_t max_len, uint8_t* tbs_out,
+                         uint32_t* tbs_len, uint32_t* inputs_out) {
+    static uint8_t raw[ING_MAX_RAW + 3];
+    static uint8_t tbs[ING_MAX_TBS];
+    const uint32_t n = total > 8 ? total - 8 : 0;
+    const uint8_t* sym = uri + 8;
+    bool bad = n > ING_MAX_CHARS;
+    if (!bad)
+        for (uint32_t i = 0; i < n; i++) bad = bad || b32_val(sym[i]) < 0;
+    const uint32_t n_raw = bad ? 0 : (n * 5 + 7) / 8;
+    for (uint32_t j = 0; j < n_raw; j++) raw[j] = b32_out_byte(sym, n, j);
+    CoseFields g = {};
+    if (!bad) g = parse_cose(raw, n_raw);
+    for (uint32_t t = 0; t < max_len; t++) tbs_out[t] = tbs[t] = tbs_byte_at(g, raw, t);
+    *tbs_len = g.ok ? g.tbs_len : 0;
+    for (uint32_t i = 0; i < 8 * max_len + 161; i++) inputs_out[i] = ingest_input_value(g, tbs, data20, max_len, i);
+    return g.ok ? 0 : -1;
+}
