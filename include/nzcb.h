@@ -178,6 +178,32 @@ int32_t nzcb_plonk_fullprove_batch_dev(nzcb_ctx* ctx, const nzcb_circuit* c, con
                                        const void* d_inputs_le, size_t B, const uint8_t* blinders_le, nzcb_proof* out,
                                        uint8_t* public_le, int32_t* status);
 
+/* ---- verifier: snarkjs plonk.verify(vk, publicSignals, proof) -------------------------------------------
+ * (the check the exported Solidity verifier performs on chain, /root/reference/Makefile:56-57,
+ * 61-62.)  The verification key comes from a zkey file's header (section 2) or from verification_key.json as
+ * `snarkjs zkey export verificationkey` writes it. */
+typedef struct nzcb_vkey nzcb_vkey;
+int32_t nzcb_vkey_from_zkey(nzcb_ctx* ctx, const uint8_t* zkey, size_t len, nzcb_vkey** out);
+int32_t nzcb_vkey_from_json(nzcb_ctx* ctx, const char* json, size_t len, nzcb_vkey** out);
+void nzcb_vkey_free(nzcb_vkey* vk);
+/* B proofs against one key, one warp per proof.  public_le: B x n_public x 32 B LE (reduced mod r as
+ * Fr.fromObject does); valid[i] = 1 (plonk.verify -> true) or 0: a point off the curve, a coordinate or
+ * evaluation out of range, n_public != vk.nPublic, or the pairing check e(-A1, X_2) e(B1, [1]_2) != 1. */
+int32_t nzcb_plonk_verify_batch(nzcb_ctx* ctx, const nzcb_vkey* vk, const nzcb_proof* proofs, const uint8_t* public_le,
+                                uint32_t n_public, size_t B, int32_t* valid);
+/* ffjavascript curve.pairingEq(P_0, Q_0, .., P_{n-1}, Q_{n-1}): *result = 1 iff prod e(P_i, Q_i) == 1, n <= 32.
+ * g1: n x 64 B affine LEM; g2: n x 128 B affine LEM (x.c0 x.c1 y.c0 y.c1, the zkey's X_2 layout; infinity = zeros).
+ * gt_out_lem (may be NULL): the product after the final exponentiation, 12 x 32 B LEM as the coefficients
+ * (c0, c1) of 1, w, .., w^5 in Fq2[w]/(w^6 - (9 + u)). */
+int32_t nzcb_pairing_eq(nzcb_ctx* ctx, const uint8_t* g1_affine_lem, const uint8_t* g2_affine_lem, uint32_t n,
+                        int32_t* result, uint8_t* gt_out_lem);
+/* [tau]G2 of the insecure known-trapdoor SRS (the tauG2 point a .ptau carries and `plonk setup` copies into the
+ * zkey header as X_2); 128 B affine LEM */
+int32_t nzcb_srs_g2(nzcb_ctx* ctx, const uint8_t tau_le[32], uint8_t out_affine_lem[128]);
+/* `snarkjs zkey export soliditycalldata` (plonk): 0x<proof bytes>,["0x<pub>",..]; NULL buf -> size in *len */
+int32_t nzcb_proof_to_calldata(const nzcb_proof* proof, const uint8_t* public_le, uint32_t n_public, char* buf,
+                               size_t* len);
+
 /* ---- pass ingest: the host helpers the reference's tests run before calculateWitness ---------------------
  * getCOSE + encodeToBeSigned (/root/reference/test/helpers/nzcp.js:9-24 base32ToBytes, :58-105 decodeCBORStream,
  * :141-172 decodeBytes / decodeCOSE, :180-206 encodeToBeSigned) and the input object of test/nzcp.js:36-41

@@ -72,6 +72,13 @@ SIGNATURES = {
     "nzcb_witness_batch": (_i32, [_vp, _vp, _vp, _sz, _vp, _vp]),
     "nzcb_plonk_fullprove_batch": (_i32, [_vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp]),
     "nzcb_plonk_fullprove_batch_dev": (_i32, [_vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp]),
+    "nzcb_vkey_from_zkey": (_i32, [_vp, _vp, _sz, ctypes.POINTER(_vp)]),
+    "nzcb_vkey_from_json": (_i32, [_vp, _cp, _sz, ctypes.POINTER(_vp)]),
+    "nzcb_vkey_free": (None, [_vp]),
+    "nzcb_plonk_verify_batch": (_i32, [_vp, _vp, _vp, _vp, _u32, _sz, _vp]),
+    "nzcb_pairing_eq": (_i32, [_vp, _vp, _vp, _u32, ctypes.POINTER(_i32), _vp]),
+    "nzcb_srs_g2": (_i32, [_vp, _vp, _vp]),
+    "nzcb_proof_to_calldata": (_i32, [ctypes.POINTER(Proof), _vp, _u32, _vp, ctypes.POINTER(_sz)]),
     "nzcb_pass_ingest_batch": (_i32, [_vp, _vp, _vp, _sz, _vp, _u32, _vp, _vp, _vp, _vp]),
     "nzcb_pass_ingest_batch_dev": (_i32, [_vp, _vp, _vp, _sz, _vp, _u32, _vp, _vp]),
     "nzcb_plonk_fullprove_uri_batch": (_i32, [_vp, _vp, _vp, _vp, _vp, _sz, _vp, _u32, _vp, _vp, _vp, _vp]),

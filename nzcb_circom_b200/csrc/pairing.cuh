@@ -1,0 +1,330 @@
+// BN254 optimal ate pairing for the device verifier: Fq2 = Fq[u]/(u^2+1), Fq12 = Fq2[w]/(w^6 - xi), xi = 9 + u,
+// G2 on the D-type twist y^2 = x^3 + 3/xi.  Replaces what snarkjs 0.4.12 plonk.verify reaches through
+// curve.pairingEq (ffjavascript 0.2.48 -> wasmcurves 0.1.0 bn128 pairing; un-vendored,
+// /root/reference/yarn.lock:3905,8173).  Host + device like fp.cuh, so the very same code is
+// checked against oracle/pairing.py on the CPU (tests/hostcheck).
+//
+// One verification is a chain of ~50 k dependent Fq multiplications on one thread; throughput comes from the
+// batch (one warp per proof, verify.cu).  Fq12 is kept flat (six Fq2 coefficients of 1, w, .., w^5): products are
+// schoolbook with the w^6 = xi fold, the Miller lines are sparse (1, w, w^3).  The big routines are deliberately
+// not inlined -- the carry-chain multiply is ~300 instructions and there are 108 of them in an Fq12 product.
+#pragma once
+#include "g1.cuh"
+#include "pairing_consts.cuh"
+
+#ifdef __CUDACC__
+#define NZ_HDN __host__ __device__ __noinline__
+#else
+#define NZ_HDN inline
+#endif
+
+namespace nzcb {
+
+struct Fq2 {
+    Fq c0, c1;
+    static NZ_HD Fq2 zero() { return Fq2{Fq::zero(), Fq::zero()}; }
+    static NZ_HD Fq2 one() { return Fq2{Fq::one(), Fq::zero()}; }
+    NZ_HD bool is_zero() const { return c0.is_zero() && c1.is_zero(); }
+    NZ_HD bool operator==(const Fq2& b) const { return c0 == b.c0 && c1 == b.c1; }
+    friend NZ_HD Fq2 operator+(const Fq2& a, const Fq2& b) { return Fq2{a.c0 + b.c0, a.c1 + b.c1}; }
+    friend NZ_HD Fq2 operator-(const Fq2& a, const Fq2& b) { return Fq2{a.c0 - b.c0, a.c1 - b.c1}; }
+    NZ_HD Fq2 neg() const { return Fq2{c0.neg(), c1.neg()}; }
+    NZ_HD Fq2 conj() const { return Fq2{c0, c1.neg()}; }
+    NZ_HD Fq2 dbl() const { return Fq2{c0.dbl(), c1.dbl()}; }
+    NZ_HD Fq2 scale(const Fq& k) const { return Fq2{c0 * k, c1 * k}; }
+    // (9 + u)(c0 + c1 u) = (9 c0 - c1) + (9 c1 + c0) u
+    NZ_HD Fq2 mul_xi() const {
+        const Fq n0 = c0.dbl().dbl().dbl() + c0, n1 = c1.dbl().dbl().dbl() + c1;
+        return Fq2{n0 - c1, n1 + c0};
+    }
+};
+
+// Karatsuba: 3 Fq products
+NZ_HDN Fq2 f2_mul(const Fq2& a, const Fq2& b) {
+    const Fq t0 = a.c0 * b.c0, t1 = a.c1 * b.c1;
+    return Fq2{t0 - t1, (a.c0 + a.c1) * (b.c0 + b.c1) - t0 - t1};
+}
+NZ_HDN Fq2 f2_sqr(const Fq2& a) {
+    const Fq t = a.c0 * a.c1;
+    return Fq2{(a.c0 + a.c1) * (a.c0 - a.c1), t.dbl()};
+}
+NZ_HDN Fq2 f2_inv(const Fq2& a) {
+    const Fq d = (a.c0.sqr() + a.c1.sqr()).inv();
+    return Fq2{a.c0 * d, (a.c1 * d).neg()};
+}
+// xi^(m (p^k - 1)/6), k = 1..3
+NZ_HD Fq2 f2_gamma(int k, int m) {
+    Fq2 r;
+    for (int i = 0; i < 8; i++) {
+        r.c0.v[i] = pairing_gamma(k - 1, m, 0, i);
+        r.c1.v[i] = pairing_gamma(k - 1, m, 1, i);
+    }
+    return r;
+}
+NZ_HD Fq2 f2_twist_b() {
+    Fq2 r;
+    for (int i = 0; i < 8; i++) {
+        r.c0.v[i] = pairing_twist_b(0, i);
+        r.c1.v[i] = pairing_twist_b(1, i);
+    }
+    return r;
+}
+
+// ---- G2 -------------------------------------------------------------------------
+struct G2Affine {
+    Fq2 x, y;
+    NZ_HD bool is_inf() const { return x.is_zero() && y.is_zero(); }
+};
+struct G2Proj {  // x = X/Z, y = Y/Z; infinity: Z = 0
+    Fq2 X, Y, Z;
+    NZ_HD bool is_inf() const { return Z.is_zero(); }
+};
+NZ_HD G2Affine g2_generator() {
+    G2Affine g;
+    for (int i = 0; i < 8; i++) {
+        g.x.c0.v[i] = pairing_g2_gen(0, 0, i);
+        g.x.c1.v[i] = pairing_g2_gen(0, 1, i);
+        g.y.c0.v[i] = pairing_g2_gen(1, 0, i);
+        g.y.c1.v[i] = pairing_g2_gen(1, 1, i);
+    }
+    return g;
+}
+NZ_HDN bool g2_on_curve(const G2Affine& q) {
+    if (q.is_inf()) return true;
+    return f2_sqr(q.y) == f2_mul(f2_sqr(q.x), q.x) + f2_twist_b();
+}
+
+// Miller line through the untwisted points, evaluated at P in G1 and scaled by an Fq2 factor (which the final
+// exponentiation removes):  l = l0 + l1 w + l3 w^3
+struct Line {
+    Fq2 l0, l1, l3;
+};
+
+// T <- 2T; tangent at T.  With A = 3X^2, B = 2YZ (slope A/B):
+//   l = B Z yP - A Z xP w + (A X - Y B) w^3
+//   N = A^2 Z - 2 X B^2;  X3 = N B;  Y3 = A (X B^2 - N) - Y B^3;  Z3 = B^3 Z
+NZ_HDN Line g2_dbl_line(G2Proj& T, const Fq& xp, const Fq& yp) {
+    const Fq2 X2 = f2_sqr(T.X);
+    const Fq2 A = X2.dbl() + X2;
+    const Fq2 B = f2_mul(T.Y, T.Z).dbl();
+    const Fq2 BZ = f2_mul(B, T.Z), AZ = f2_mul(A, T.Z);
+    Line l;
+    l.l0 = BZ.scale(yp);
+    l.l1 = AZ.scale(xp).neg();
+    l.l3 = f2_mul(A, T.X) - f2_mul(T.Y, B);
+    const Fq2 B2 = f2_sqr(B);
+    const Fq2 XB2 = f2_mul(T.X, B2);
+    const Fq2 N = f2_mul(A, AZ) - XB2.dbl();
+    const Fq2 B3 = f2_mul(B2, B);
+    const Fq2 Y3 = f2_mul(A, XB2 - N) - f2_mul(T.Y, B3);
+    T.X = f2_mul(N, B);
+    T.Y = Y3;
+    T.Z = f2_mul(B3, T.Z);
+    return l;
+}
+
+// T <- T + Q (Q affine, T != +-Q); chord through T and Q.  With E = y2 Z - Y, F = x2 Z - X (slope E/F):
+//   l = F yP - E xP w + (E x2 - F y2) w^3
+//   D = F^2 Z;  N = E^2 Z - F^2 (X + x2 Z);  X3 = N F;  Y3 = E (x2 D - N) - y2 F D;  Z3 = F D
+NZ_HDN Line g2_add_line(G2Proj& T, const G2Affine& Q, const Fq& xp, const Fq& yp) {
+    const Fq2 x2Z = f2_mul(Q.x, T.Z);
+    const Fq2 E = f2_mul(Q.y, T.Z) - T.Y, F = x2Z - T.X;
+    Line l;
+    l.l0 = F.scale(yp);
+    l.l1 = E.scale(xp).neg();
+    l.l3 = f2_mul(E, Q.x) - f2_mul(F, Q.y);
+    const Fq2 F2 = f2_sqr(F);
+    const Fq2 D = f2_mul(F2, T.Z);
+    const Fq2 N = f2_mul(f2_sqr(E), T.Z) - f2_mul(F2, T.X + x2Z);
+    const Fq2 FD = f2_mul(F, D);
+    const Fq2 Y3 = f2_mul(E, f2_mul(Q.x, D) - N) - f2_mul(Q.y, FD);
+    T.X = f2_mul(N, F);
+    T.Y = Y3;
+    T.Z = FD;
+    return l;
+}
+
+NZ_HDN G2Affine g2_to_affine(const G2Proj& T) {
+    if (T.is_inf()) return G2Affine{Fq2::zero(), Fq2::zero()};
+    const Fq2 zi = f2_inv(T.Z);
+    return G2Affine{f2_mul(T.X, zi), f2_mul(T.Y, zi)};
+}
+
+// k * Q, k given as 8 little-endian u32 limbs (double-and-add from the top bit; Q of prime order r > k)
+NZ_HDN G2Affine g2_mul_limbs(const G2Affine& Q, const uint32_t* k) {
+    G2Proj T{Fq2::zero(), Fq2::one(), Fq2::zero()};
+    if (Q.is_inf()) return Q;
+    const Fq zero = Fq::zero();
+    bool started = false;
+    for (int i = 255; i >= 0; i--) {
+        if (started) g2_dbl_line(T, zero, zero);
+        if ((k[i >> 5] >> (i & 31)) & 1) {
+            if (!started) {
+                T = G2Proj{Q.x, Q.y, Fq2::one()};
+                started = true;
+            } else {
+                g2_add_line(T, Q, zero, zero);
+            }
+        }
+    }
+    return g2_to_affine(T);
+}
+
+// ---- Fq12 -----------------------------------------------------------------------
+struct Fq12 {
+    Fq2 c[6];
+    static NZ_HD Fq12 one() {
+        Fq12 r;
+        r.c[0] = Fq2::one();
+        for (int i = 1; i < 6; i++) r.c[i] = Fq2::zero();
+        return r;
+    }
+    NZ_HD bool is_one() const {
+        bool ok = c[0] == Fq2::one();
+        for (int i = 1; i < 6; i++) ok = ok && c[i].is_zero();
+        return ok;
+    }
+    NZ_HD bool operator==(const Fq12& b) const {
+        bool ok = true;
+        for (int i = 0; i < 6; i++) ok = ok && c[i] == b.c[i];
+        return ok;
+    }
+    // a^(p^6): w -> -w
+    NZ_HD Fq12 conj() const {
+        Fq12 r;
+        for (int i = 0; i < 6; i++) r.c[i] = (i & 1) ? c[i].neg() : c[i];
+        return r;
+    }
+};
+
+NZ_HD void f12_fold(const Fq2* t, Fq12& r) {
+    for (int k = 0; k < 5; k++) r.c[k] = t[k] + t[k + 6].mul_xi();
+    r.c[5] = t[5];
+}
+
+NZ_HDN Fq12 f12_mul(const Fq12& a, const Fq12& b) {
+    Fq2 t[11];
+    for (int k = 0; k < 11; k++) t[k] = Fq2::zero();
+#pragma unroll 1
+    for (int i = 0; i < 6; i++)
+#pragma unroll 1
+        for (int j = 0; j < 6; j++) t[i + j] = t[i + j] + f2_mul(a.c[i], b.c[j]);
+    Fq12 r;
+    f12_fold(t, r);
+    return r;
+}
+
+NZ_HDN Fq12 f12_sqr(const Fq12& a) {
+    Fq2 t[11];
+    for (int k = 0; k < 11; k++) t[k] = Fq2::zero();
+#pragma unroll 1
+    for (int i = 0; i < 6; i++) {
+        t[2 * i] = t[2 * i] + f2_sqr(a.c[i]);
+#pragma unroll 1
+        for (int j = i + 1; j < 6; j++) t[i + j] = t[i + j] + f2_mul(a.c[i], a.c[j]).dbl();
+    }
+    Fq12 r;
+    f12_fold(t, r);
+    return r;
+}
+
+// a * (l0 + l1 w + l3 w^3): 18 Fq2 products
+NZ_HDN Fq12 f12_mul_line(const Fq12& a, const Line& l) {
+    Fq2 t[11];
+    for (int k = 0; k < 11; k++) t[k] = Fq2::zero();
+#pragma unroll 1
+    for (int i = 0; i < 6; i++) {
+        t[i] = t[i] + f2_mul(a.c[i], l.l0);
+        t[i + 1] = t[i + 1] + f2_mul(a.c[i], l.l1);
+        t[i + 3] = t[i + 3] + f2_mul(a.c[i], l.l3);
+    }
+    Fq12 r;
+    f12_fold(t, r);
+    return r;
+}
+
+// a^(p^k), k = 1..3: the coefficient of w^m becomes conj^k(c_m) * xi^(m (p^k - 1)/6)
+NZ_HDN Fq12 f12_frob(const Fq12& a, int k) {
+    Fq12 r;
+    r.c[0] = (k == 2) ? a.c[0] : a.c[0].conj();
+#pragma unroll 1
+    for (int m = 1; m < 6; m++)
+        r.c[m] = f2_mul((k == 2) ? a.c[m] : a.c[m].conj(), f2_gamma(k, m));
+    return r;
+}
+
+// a^-1 = conj(a) / (a conj(a)); the norm lies in Fq6 = Fq2[v]/(v^3 - xi), v = w^2
+NZ_HDN Fq12 f12_inv(const Fq12& a) {
+    const Fq12 cj = a.conj();
+    const Fq12 n = f12_mul(a, cj);
+    const Fq2 a0 = n.c[0], a1 = n.c[2], a2 = n.c[4];
+    const Fq2 t0 = f2_sqr(a0) - f2_mul(a1, a2).mul_xi();
+    const Fq2 t1 = f2_sqr(a2).mul_xi() - f2_mul(a0, a1);
+    const Fq2 t2 = f2_sqr(a1) - f2_mul(a0, a2);
+    const Fq2 d = f2_mul(a0, t0) + (f2_mul(a2, t1) + f2_mul(a1, t2)).mul_xi();
+    const Fq2 di = f2_inv(d);
+    Fq12 i6;
+    i6.c[0] = f2_mul(t0, di);
+    i6.c[2] = f2_mul(t1, di);
+    i6.c[4] = f2_mul(t2, di);
+    i6.c[1] = i6.c[3] = i6.c[5] = Fq2::zero();
+    return f12_mul(cj, i6);
+}
+
+NZ_HDN Fq12 f12_pow_u64(const Fq12& a, uint64_t e) {
+    Fq12 r = Fq12::one();
+    bool started = false;
+    for (int i = 63; i >= 0; i--) {
+        if (started) r = f12_sqr(r);
+        if ((e >> i) & 1) {
+            r = started ? f12_mul(r, a) : a;
+            started = true;
+        }
+    }
+    return r;
+}
+
+// f_{6x+2,Q}(P) l_{T,pi(Q)}(P) l_{T+pi(Q),-pi^2(Q)}(P); 1 when either point is infinity
+NZ_HDN Fq12 miller_loop(const G1Affine& P, const G2Affine& Q) {
+    Fq12 f = Fq12::one();
+    if (P.is_inf() || Q.is_inf()) return f;
+    G2Proj T{Q.x, Q.y, Fq2::one()};
+#pragma unroll 1
+    for (int i = 63; i >= 0; i--) {
+        f = f12_sqr(f);
+        f = f12_mul_line(f, g2_dbl_line(T, P.x, P.y));
+        if ((PAIRING_ATE_LOW >> i) & 1) f = f12_mul_line(f, g2_add_line(T, Q, P.x, P.y));
+    }
+    // pi(Q) = (conj(x) gamma_1^2, conj(y) gamma_1^3);  -pi^2(Q) = (x gamma_2^2, y)  since xi^((p^2-1)/2) = -1
+    G2Affine Q1{f2_mul(Q.x.conj(), f2_gamma(1, 2)), f2_mul(Q.y.conj(), f2_gamma(1, 3))};
+    G2Affine Q2n{f2_mul(Q.x, f2_gamma(2, 2)), Q.y};
+    f = f12_mul_line(f, g2_add_line(T, Q1, P.x, P.y));
+    f = f12_mul_line(f, g2_add_line(T, Q2n, P.x, P.y));
+    return f;
+}
+
+// f^((p^12 - 1)/r): easy part (p^6 - 1)(p^2 + 1), then the hard part (p^4 - p^2 + 1)/r by the addition chain of
+// Scott et al. (three powers by x and Frobenius maps; equal to the plain power, checked in oracle/pairing.py)
+NZ_HDN Fq12 final_exp(const Fq12& f0) {
+    Fq12 f = f12_mul(f0.conj(), f12_inv(f0));
+    f = f12_mul(f12_frob(f, 2), f);
+    const Fq12 fx = f12_pow_u64(f, PAIRING_BN_X);
+    const Fq12 fx2 = f12_pow_u64(fx, PAIRING_BN_X);
+    const Fq12 fx3 = f12_pow_u64(fx2, PAIRING_BN_X);
+    const Fq12 y0 = f12_mul(f12_mul(f12_frob(f, 1), f12_frob(f, 2)), f12_frob(f, 3));
+    const Fq12 y1 = f.conj();
+    const Fq12 y2 = f12_frob(fx2, 2);
+    const Fq12 y3 = f12_frob(fx, 1).conj();
+    const Fq12 y4 = f12_mul(fx, f12_frob(fx2, 1)).conj();
+    const Fq12 y5 = fx2.conj();
+    const Fq12 y6 = f12_mul(fx3, f12_frob(fx3, 1)).conj();
+    Fq12 t0 = f12_mul(f12_mul(f12_sqr(y6), y4), y5);
+    Fq12 t1 = f12_mul(f12_mul(y3, y5), t0);
+    t0 = f12_mul(t0, y2);
+    t1 = f12_sqr(f12_mul(f12_sqr(t1), t0));
+    t0 = f12_mul(t1, y1);
+    t1 = f12_mul(t1, y0);
+    return f12_mul(t1, f12_sqr(t0));
+}
+
+}  // namespace nzcb

@@ -99,3 +99,22 @@ class G1Table:
             self.close()
         except Exception:
             pass
+
+
+def pairingEq(*args, ctx=None, want_gt=False):
+    """curve.pairingEq(P_0, Q_0, P_1, Q_1, ...): prod e(P_i, Q_i) == 1.  P_i: 64 B G1 affine LEM, Q_i: 128 B G2 affine
+    LEM (x.c0 x.c1 y.c0 y.c1).  want_gt: also return the GT product (384 B, coefficients of 1, w, .., w^5)."""
+    ctx = ctx or default_context()
+    if len(args) % 2:
+        raise ValueError("Pairing arguments must be even")  # ffjavascript's message
+    n = len(args) // 2
+    g1 = b"".join(bytes(args[2 * i]) for i in range(n))
+    g2 = b"".join(bytes(args[2 * i + 1]) for i in range(n))
+    if len(g1) != 64 * n or len(g2) != 128 * n:
+        raise ValueError("pairingEq takes 64-byte G1 and 128-byte G2 points")
+    res = ctypes.c_int32(0)
+    gt = (ctypes.c_uint8 * 384)()
+    b1 = (ctypes.c_uint8 * max(1, len(g1))).from_buffer_copy(g1 or b"\0")
+    b2 = (ctypes.c_uint8 * max(1, len(g2))).from_buffer_copy(g2 or b"\0")
+    ctx.check(ctx.lib.nzcb_pairing_eq(ctx.h, b1, b2, n, ctypes.byref(res), gt))
+    return (bool(res.value), bytes(gt)) if want_gt else bool(res.value)

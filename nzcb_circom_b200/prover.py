@@ -30,7 +30,7 @@ class CircuitProver:
         self.vk = None
         self.verbose = verbose
 
-    def setup(self, srs_g1_lem=None, keep_zkey=False):
+    def setup(self, srs_g1_lem=None, keep_zkey=False, x2_g2_lem=None):
         """powersoftau + plonk setup on the GPU, zkey made device resident; returns the vk object
         (or the zkey file bytes with keep_zkey=True, for callers that also want to write it out)"""
         from .snarkjs import R_MOD as _R
@@ -47,7 +47,9 @@ class CircuitProver:
             srs_g1_lem = powersoftau.new_g1(self.tau % _R, (1 << power) + 6, self.ctx)
         self.timings["srs"] = time.time() - t
         t = time.time()
-        zkey = plonk.setup(r1cs, srs_g1_lem, bytes(128), self.ctx)
+        # X_2 = [tau]_2 when the trapdoor is known (the synthetic SRS); an external SRS must bring its own
+        x2 = powersoftau.new_g2(self.tau % _R, self.ctx) if self.tau is not None and x2_g2_lem is None else (x2_g2_lem or bytes(128))
+        zkey = plonk.setup(r1cs, srs_g1_lem, x2, self.ctx)
         self.timings["setup"] = time.time() - t
         t = time.time()
         self.vk = zKey.exportVerificationKey(zkey)
@@ -73,6 +75,14 @@ class CircuitProver:
     def prove_raw(self, inputs_le, B, blinders_list=None, device_inputs=None):
         return plonk.fullProveRaw(inputs_le, B, self.tester._handle(self.ctx), self.zk, blinders_list, self.ctx,
                                   device_inputs)
+
+    def verify(self, publics_list, proofs):
+        """plonk.verify of B proofs against this circuit's key, on the GPU -> [bool]"""
+        from .snarkjs import VKey
+
+        if getattr(self, "_vkey", None) is None:
+            self._vkey = VKey(self.vk, self.ctx)
+        return plonk.verify_batch(self._vkey, publics_list, proofs, self.ctx)
 
     def marshal(self, inputs):
         """host-side marshalling of input dicts to the B x nInputs x 32 B buffer the C ABI takes"""

@@ -98,6 +98,47 @@ def proof_struct_to_obj(ps: Proof):
     return obj
 
 
+def proof_obj_to_bytes(obj):
+    """the proof object of plonk.prove / proof.json -> the 800-byte nzcb_proof layout.  Coordinates and evaluations
+    must fit 32 bytes; range and curve checks are the verifier's."""
+    def pt(v):
+        if str(v[2]) == "0":
+            return bytes(64)
+        return int(v[0]).to_bytes(32, "big") + int(v[1]).to_bytes(32, "big")
+
+    out = b"".join(pt(obj[k]) for k in ("A", "B", "C", "Z", "T1", "T2", "T3", "Wxi", "Wxiw"))
+    return out + b"".join(int(obj[k]).to_bytes(32, "big") for k in _EVALS)
+
+
+class VKey:
+    """a verification key resident on the GPU (nzcb_vkey); built from the vk object / JSON text of
+    `snarkjs zkey export verificationkey` or straight from zkey bytes"""
+
+    def __init__(self, vk, ctx=None):
+        import json as _json
+
+        self.ctx = ctx or default_context()
+        h = ctypes.c_void_p()
+        if isinstance(vk, (bytes, bytearray, memoryview)) and bytes(vk[:4]) == b"zkey":
+            self.ctx.check(self.ctx.lib.nzcb_vkey_from_zkey(self.ctx.h, as_cbuf(bytes(vk)), len(vk), ctypes.byref(h)))
+        else:
+            text = vk if isinstance(vk, str) else (_json.dumps(vk, indent=1) if isinstance(vk, dict) else bytes(vk).decode())
+            raw = text.encode()
+            self.ctx.check(self.ctx.lib.nzcb_vkey_from_json(self.ctx.h, raw, len(raw), ctypes.byref(h)))
+        self.h = h
+
+    def close(self):
+        if self.h and self.ctx.h:
+            self.ctx.lib.nzcb_vkey_free(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def _blinder_buf(blinders):
     if blinders is None:
         return None
@@ -144,6 +185,51 @@ class _Plonk:
             public = [str(int.from_bytes(pb[k * 32:(k + 1) * 32], "little")) for k in range(zk.n_public)]
             res.append((bytes(out[i]) if status[i] == 0 else None, public, int(status[i])))
         return res
+
+    def verify(self, vk, publicSignals, proof, ctx=None):
+        """snarkjs.plonk.verify(vk_verifier, publicSignals, proof) -> bool.  vk: a VKey, the vk object / JSON text or
+        zkey bytes; proof: the proof object or the 800 raw bytes."""
+        return self.verify_batch(vk, [publicSignals], [proof], ctx)[0]
+
+    def verify_batch(self, vk, publics_list, proofs, ctx=None):
+        """B proofs against one key -> [bool]; one warp per proof on the GPU"""
+        own = not isinstance(vk, VKey)
+        vkey = VKey(vk, ctx) if own else vk
+        ctx = vkey.ctx
+        try:
+            B = len(proofs)
+            if B == 0:
+                return []
+            n_pub = len(publics_list[0])
+            if any(len(p) != n_pub for p in publics_list):
+                raise ValueError("every proof of a batch must carry the same number of public signals")
+            raw = b"".join(p if isinstance(p, (bytes, bytearray)) else proof_obj_to_bytes(p) for p in proofs)
+            if len(raw) != 800 * B:
+                raise ValueError("a raw proof is 800 bytes")
+            pubs = b"".join((int(x) % (1 << 256)).to_bytes(32, "little") for ps in publics_list for x in ps)
+            valid = (ctypes.c_int32 * B)()
+            ctx.check(ctx.lib.nzcb_plonk_verify_batch(ctx.h, vkey.h, as_cbuf(raw), as_cbuf(pubs or b"\0"), n_pub, B, valid))
+            return [bool(v) for v in valid]
+        finally:
+            if own:
+                vkey.close()
+
+    def exportSolidityCallData(self, proof, publicSignals):
+        """`snarkjs zkey export soliditycalldata` for a plonk proof (/root/reference/Makefile:57,62 export the
+        verifier this text is fed to)"""
+        from ._lib import load
+
+        lib = load()
+        raw = proof if isinstance(proof, (bytes, bytearray)) else proof_obj_to_bytes(proof)
+        ps = Proof.from_buffer_copy(raw)
+        pubs = b"".join(int(x).to_bytes(32, "little") for x in publicSignals)
+        n = ctypes.c_size_t(0)
+        lib.nzcb_proof_to_calldata(ctypes.byref(ps), as_cbuf(pubs or b"\0"), len(publicSignals), None, ctypes.byref(n))
+        buf = ctypes.create_string_buffer(n.value)
+        rc = lib.nzcb_proof_to_calldata(ctypes.byref(ps), as_cbuf(pubs or b"\0"), len(publicSignals), buf, ctypes.byref(n))
+        if rc != 0:
+            raise NzcbError(rc, "proof_to_calldata failed")
+        return buf.value.decode()
 
     def proof_json(self, proof_bytes, ctx=None):
         """proof.json text exactly as snarkjs writes it (JSON.stringify(proof, null, 1))."""
@@ -288,6 +374,14 @@ class _Powersoftau:
         ctx.check(ctx.lib.nzcb_srs_g1(ctx.h, t, count, out))
         return bytes(out)
 
+
+    def new_g2(self, tau, ctx=None):
+        """[tau]G2 as 128 affine LEM bytes: the tauG2 point of the same insecure SRS, X_2 of the zkey header"""
+        ctx = ctx or default_context()
+        t = (ctypes.c_uint8 * 32).from_buffer_copy(int(tau % R_MOD).to_bytes(32, "little"))
+        out = (ctypes.c_uint8 * 128)()
+        ctx.check(ctx.lib.nzcb_srs_g2(ctx.h, t, out))
+        return bytes(out)
 
     def lagrange_g1(self, srs_g1_lem, power, ctx=None):
         """[L_i(tau)]G1 for the 2^power domain from the tauG1 points: the Lagrange section `snarkjs powersoftau

@@ -507,18 +507,20 @@ def vk_from_json(j):
     return vk
 
 
-def verify_with_trapdoor(vk, public, proof, tau):
-    """plonk.verify with the final pairing e(W1, [tau]_2) == e(W2, [1]_2) replaced by the
-    equivalent G1 identity tau * W1 == W2, valid because the SRS trapdoor tau is known."""
+def _verify_points(vk, public, proof):
+    """everything of plonk.verify up to the pairing: -> (A1, B1) with the proof accepted iff
+    e(A1, X_2) == e(B1, [1]_2); None when the proof is not well constructed"""
     n = 1 << vk["power"]
     for k in PROOF_POINTS:
+        if proof[k] is not None and not (0 <= proof[k][0] < b.P_MOD and 0 <= proof[k][1] < b.P_MOD):
+            return None
         if not b.g1_is_on_curve(proof[k]):
-            return False
+            return None
     for k in PROOF_EVALS:
         if not (0 <= proof[k] < R):
-            return False
+            return None
     if len(public) != vk["nPublic"]:
-        return False
+        return None
     g = b.g1_to_be
     beta = hash_to_fr(b"".join(b.to_be(p % R) for p in public) + g(proof["A"]) + g(proof["B"]) + g(proof["C"]))
     gamma = hash_to_fr(b.to_be(beta))
@@ -560,4 +562,37 @@ def verify_with_trapdoor(vk, public, proof, tau):
     lhs = b.g1_add(proof["Wxi"], b.g1_mul(proof["Wxiw"], u))
     rhs = b.g1_msm_naive([proof["Wxi"], proof["Wxiw"]], [xi, u * xi % R * w % R])
     rhs = b.g1_add(rhs, b.g1_sub(F, E))
-    return b.g1_mul(lhs, tau) == rhs
+    return lhs, rhs
+
+
+def verify_with_trapdoor(vk, public, proof, tau):
+    """plonk.verify with the final pairing e(W1, [tau]_2) == e(W2, [1]_2) replaced by the
+    equivalent G1 identity tau * W1 == W2, valid because the SRS trapdoor tau is known."""
+    pts = _verify_points(vk, public, proof)
+    return pts is not None and b.g1_mul(pts[0], tau) == pts[1]
+
+
+def vk_x2(vk):
+    """X_2 of a vk as an oracle G2 point: 128 LEM bytes (zkey header) or the JSON triple of Fq2 pairs"""
+    from . import pairing as pg
+
+    x2 = vk["X_2"]
+    if isinstance(x2, (bytes, bytearray)):
+        return pg.g2_from_lem(bytes(x2))
+    if x2[2] == ["0", "0"]:
+        return None
+    return ((int(x2[0][0]), int(x2[0][1])), (int(x2[1][0]), int(x2[1][1])))
+
+
+def verify(vk, public, proof):
+    """snarkjs plonk.verify with the real pairing check
+    curve.pairingEq(-A1, X_2, B1, G2.one): e(-A1, X_2) e(B1, [1]_2) == 1"""
+    from . import pairing as pg
+
+    pts = _verify_points(vk, public, proof)
+    if pts is None:
+        return False
+    X2 = vk_x2(vk)
+    if X2 is not None and not pg.g2_is_on_curve(X2):
+        return False
+    return pg.pairing_eq([(b.g1_neg(pts[0]), X2), (pts[1], pg.G2_GEN)])

@@ -68,3 +68,35 @@ extern "C" int fc_ingest(const uint8_t* uri, uint32_t total, const uint8_t* data
     for (uint32_t i = 0; i < 8 * max_len + 161; i++) inputs_out[i] = ingest_input_value(g, tbs, data20, max_len, i);
     return g.ok ? 0 : -1;
 }
+
+// ---- pairing (csrc/pairing.cuh) ----
+#include "../../nzcb_circom_b200/csrc/pairing.cuh"
+// e(P, Q): P 64 B affine LEM, Q 128 B (x.c0 x.c1 y.c0 y.c1 LEM); out = 6 x Fq2 LEM (384 B)
+extern "C" void fc_pairing(const uint8_t* p, const uint8_t* q, uint8_t* out, int do_final) {
+    G1Affine P; memcpy(&P, p, 64);
+    G2Affine Q; memcpy(&Q, q, 128);
+    Fq12 f = miller_loop(P, Q);
+    if (do_final) f = final_exp(f);
+    memcpy(out, &f, 384);
+}
+extern "C" int fc_g2_mul(const uint8_t* q, const uint8_t* k_le, uint8_t* out) {
+    G2Affine Q; memcpy(&Q, q, 128);
+    uint32_t k[8]; memcpy(k, k_le, 32);
+    G2Affine r = g2_mul_limbs(Q, k);
+    memcpy(out, &r, 128);
+    return g2_on_curve(r) ? 1 : 0;
+}
+
+// ---- plonk.verify (csrc/verify.cuh) ----
+#include "../../nzcb_circom_b200/csrc/verify.cuh"
+extern "C" void fc_keccak256_hd(const uint8_t* data, uint32_t len, uint8_t* out) {
+    KeccakHD k; k.init(); k.update(data, len); k.finish(out);
+}
+// vk: n_public u32, power u32, k1 k2 w (LEM), 8 x G1 (LEM 64), X2 (LEM 128)
+extern "C" int fc_plonk_verify(const uint8_t* vkb, const uint8_t* proof, const uint8_t* pubs, uint32_t n_pub) {
+    VkDev vk;
+    memcpy(&vk.n_public, vkb, 4); memcpy(&vk.power, vkb + 4, 4);
+    memcpy(&vk.k1, vkb + 8, 32); memcpy(&vk.k2, vkb + 40, 32); memcpy(&vk.w, vkb + 72, 32);
+    memcpy(vk.Q, vkb + 104, 512); memcpy(&vk.X2, vkb + 616, 128);
+    return verify_serial(vk, proof, pubs, n_pub) ? 1 : 0;
+}
