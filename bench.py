@@ -84,13 +84,13 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_passes(rank, step, batch):
+def make_pass_dicts(rank, step, batch):
     from nzcb_circom_b200 import nzcp_helpers as H
-    out = []
-    for i in range(batch):
-        p = H.synth_pass(100000 * rank + 1000 * step + i)
-        out.append((p["toBeSigned"], p["data"]))
-    return out
+    return [H.synth_pass(100000 * rank + 1000 * step + i) for i in range(batch)]
+
+
+def make_passes(rank, step, batch):
+    return [(p["toBeSigned"], p["data"]) for p in make_pass_dicts(rank, step, batch)]
 
 
 def run_reference(args, rank, world):
@@ -236,6 +236,42 @@ def main():
     barrier()
     e2e = world * steps * B / e2e_s
 
+    # ---- leg 2b: the same end-to-end measurement fed with pass URIs (the QR string): base32 / COSE / ToBeSigned /
+    # input marshalling run on the device (nzcb_plonk_fullprove_uri_batch), ~0.6 KB per pass cross PCIe
+    all_uris = [[p["uri"] for p in make_pass_dicts(rank, s, B)] for s in range(warm + steps)]
+    all_data = [[d for _t, d in ps] for ps in all_passes]
+    check(pr.prove_uris(all_uris[0], all_data[0]))
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(warm, warm + steps):
+        last_uri = pr.prove_uris(all_uris[s], all_data[s])
+        check(last_uri)
+    e2e_uri_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e_uri = world * steps * B / e2e_uri_s
+    uri_bytes = sum(len(u) for u in all_uris[warm]) + 4 * (B + 1) + 20 * B
+    same_publics = [r[1] for r in last_uri] == [r[1] for r in last]
+
+    # ---- the verifier on the proofs of the last step (snarkjs plonk.verify, one warp per proof): latency of one
+    # verification, throughput of a batch of 1024
+    verify = None
+    if rank == 0:
+        pubs = [[int(x) for x in r[1]] for r in last]
+        prfs = [r[0] for r in last]
+        ok_all = all(pr.verify(pubs, prfs))
+        t0 = time.perf_counter()
+        pr.verify(pubs[:1], prfs[:1])
+        v_lat = 1000 * (time.perf_counter() - t0)
+        v_lat_dev = ctx.last_device_ms
+        reps = (1024 + B - 1) // B
+        t0 = time.perf_counter()
+        big = pr.verify(pubs * reps, prfs * reps)
+        v_wall = time.perf_counter() - t0
+        verify = {"all_valid": bool(ok_all and all(big)), "latency_ms_single": v_lat, "device_ms_single": v_lat_dev,
+                  "batch": len(big), "device_ms_batch": ctx.last_device_ms,
+                  "proofs_per_s_device": len(big) / (ctx.last_device_ms / 1000.0),
+                  "proofs_per_s_e2e": len(big) / v_wall}
+
     # ---- single-proof latency (B = 1, one lane) with the dominant kernel timed alone on the GPU
     one = pr.marshal_passes(all_passes[0][:1])
     check(pr.prove_raw(one, 1))
@@ -322,6 +358,10 @@ def main():
                        "parallelism": f"independent proofs sharded over {world} GPU(s), no collective",
                        "l2": "inputs larger than L2: each proof streams the 3 GiB resident zkey plus ~2.5 GiB of scratch"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": B * n_in * 32, "d2h_bytes_per_step": B * (800 + 96 + 4)},
+            "e2e_from_pass_uris": {"value": e2e_uri, "unit": UNIT, "h2d_bytes_per_step": uri_bytes,
+                                   "d2h_bytes_per_step": B * (800 + 96 + 4), "same_public_signals_as_e2e": same_publics,
+                                   "what": "pass URIs in, proofs out: ingest (base32, COSE, ToBeSigned, marshalling) on the device"},
+            "verify": verify,
             "gpu_launches": int(gpu_launches), "clocks": clocks, "roofline": roofline, "whole_proof_roofline": whole,
             "latency_ms_single_proof": latency_ms,
             "latency_ms_single_proof_msm_split": split_latency_ms, "msm_split_proof_equals_single_gpu": split_equal,

@@ -238,6 +238,19 @@ def nzcp_decode_outputs(out):
     return nullifier_hash_part, tbs_hash, exp, o[2][6:26]
 
 
+def bytesToBase32(data):
+    """unpadded RFC 4648 base32, the inverse of base32ToBytes (what an NZCP QR code carries)"""
+    bits = "".join(f"{x:08b}" for x in data)
+    bits += "0" * (-len(bits) % 5)
+    return "".join(_B32[int(bits[i:i + 5], 2)] for i in range(0, len(bits), 5))
+
+
+def passURI(bodyProtected, payload, signature):
+    """COSE_Sign1 (tag 18, [protected, {}, payload, signature]) as an "NZCP:/1/" URI: what getCOSE parses"""
+    return "NZCP:/1/" + bytesToBase32(b"\xd2\x84" + _encodeBytes(bodyProtected) + b"\xa0" + _encodeBytes(payload)
+                                      + _encodeBytes(signature))
+
+
 # ---- synthetic passes (SURVEY.md 8d: no network, no real passes) -----------
 # bytes 76..246 of the example ToBeSigned: the fixed 171-byte "vc" map prefix up to and including the
 # credentialSubject map header (a3); CREDENTIAL_SUBJECT_VC_OFFSET = 171 (nzcptpl.circom:461)
@@ -292,5 +305,6 @@ def synth_pass(seed, live=True):
         if not ok:
             continue
         data = bytes(rng.randrange(256) for _ in range(20))
+        sig = bytes(rng.randrange(256) for _ in range(64))  # never checked by the circuit (the contract does that)
         return {"toBeSigned": tbs, "nullifier": f"{given},{family},{dob}", "exp": exp, "nbf": nbf, "data": data,
-                "maxLen": max_len}
+                "maxLen": max_len, "uri": passURI(protected, payload, sig)}
