@@ -127,6 +127,17 @@ int32_t nzcb_srs_g1(nzcb_ctx* ctx, const uint8_t tau_le[32], size_t count, uint8
 int32_t nzcb_plonk_setup(nzcb_ctx* ctx, const uint8_t* r1cs, size_t r1cs_len, const uint8_t* srs_g1_lem,
                          size_t srs_count, const uint8_t x2_g2_lem[128], uint8_t* zkey_out, size_t* zkey_len);
 
+/* the same from the .ptau file itself: `snarkjs plonk setup circuit.r1cs pot.ptau circuit.zkey`
+ * (/root/reference/Makefile:55,60; README.md:41).  Takes tauG1[0 .. 2^cirPower + 6) of section 2 and tauG2[1] of
+ * section 3; fails with snarkjs' messages "Powers of tau is not prepared." (no section 12) and "circuit too big
+ * for this power of tau ceremony." */
+int32_t nzcb_plonk_setup_ptau(nzcb_ctx* ctx, const uint8_t* r1cs, size_t r1cs_len, const uint8_t* ptau, size_t ptau_len,
+                              uint8_t* zkey_out, size_t* zkey_len);
+/* header of a .ptau (no GPU needed): power, ceremonyPower, points in the tauG1 section, whether
+ * `powersoftau prepare phase2` has run (section 12 present); any pointer may be NULL */
+int32_t nzcb_ptau_info(const uint8_t* ptau, size_t len, uint32_t* power, uint32_t* ceremony_power, uint64_t* n_tau_g1,
+                       int32_t* prepared);
+
 /* what the R1CS -> PLONK expansion of `plonk setup` yields for this r1cs: gate count, additions,
  * PLONK signal count and log2 of the domain (so the caller can size the SRS: 2^power + 6 points) */
 int32_t nzcb_plonk_setup_info(nzcb_ctx* ctx, const uint8_t* r1cs, size_t r1cs_len, uint32_t* n_gates,

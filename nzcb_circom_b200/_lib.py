@@ -59,6 +59,9 @@ SIGNATURES = {
     "nzcb_msm_g1_dev": (_i32, [_vp, _vp, _vp, _sz, _vp]),
     "nzcb_srs_g1": (_i32, [_vp, _vp, _sz, _vp]),
     "nzcb_plonk_setup": (_i32, [_vp, _vp, _sz, _vp, _sz, _vp, _vp, ctypes.POINTER(_sz)]),
+    "nzcb_plonk_setup_ptau": (_i32, [_vp, _vp, _sz, _vp, _sz, _vp, ctypes.POINTER(_sz)]),
+    "nzcb_ptau_info": (_i32, [_vp, _sz, ctypes.POINTER(_u32), ctypes.POINTER(_u32), ctypes.POINTER(ctypes.c_uint64),
+                              ctypes.POINTER(_i32)]),
     "nzcb_plonk_setup_info": (_i32, [_vp, _vp, _sz] + [ctypes.POINTER(_u32)] * 4),
     "nzcb_zkey_load": (_i32, [_vp, _vp, _sz, ctypes.POINTER(_vp)]),
     "nzcb_zkey_free": (None, [_vp]),

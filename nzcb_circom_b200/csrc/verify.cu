@@ -7,6 +7,7 @@
 // the twenty scalars; lanes 0..19 each do one G1 scalar multiplication; lanes 0 and 1 add up B1 and A1 and run one
 // Miller loop each; lane 0 multiplies the two and does the final exponentiation.  A verification is latency-bound
 // (a chain of ~50 k dependent Fq multiplications), so throughput comes from the batch: B proofs = B warps.
+#include <stdlib.h>
 #include "common.cuh"
 #include "verify.cuh"
 
@@ -20,9 +21,12 @@ struct nzcb_vkey {
 
 namespace {
 
+// serial = 0: one warp per proof, the scalar multiplications and the two Miller loops spread over the lanes.
+// serial = 1 (NZCB_VERIFY_SERIAL=1): the same steps on one thread per proof (blockDim 1) -- a cross-check of the
+// lane choreography.
 __global__ void __launch_bounds__(32) k_plonk_verify(const VkDev* __restrict__ vkp, const uint8_t* __restrict__ proofs,
                                                      const uint8_t* __restrict__ pubs, uint32_t n_pub, uint32_t B,
-                                                     int32_t* __restrict__ valid) {
+                                                     int32_t* __restrict__ valid, int serial) {
     __shared__ G1Affine pts[VERIFY_TERMS];
     __shared__ Fr sc[VERIFY_TERMS];
     __shared__ G1XYZZ acc[VERIFY_TERMS];
@@ -40,21 +44,17 @@ __global__ void __launch_bounds__(32) k_plonk_verify(const VkDev* __restrict__ v
             __syncwarp();
             continue;
         }
-        if (lane < VERIFY_TERMS) acc[lane] = g1_mul_limbs(pts[lane], sc[lane]);
+#pragma unroll 1
+        for (uint32_t l = 0; l < VERIFY_TERMS; l++)
+            if (serial || l == lane) acc[l] = g1_mul_limbs(pts[l], sc[l]);
         __syncwarp();
-        if (lane == 0) {
-            G1XYZZ s = acc[0];
-            for (int i = 1; i < 18; i++) s.add(acc[i]);
-            ab[1] = s.to_affine();
-        } else if (lane == 1) {
-            G1XYZZ s = acc[18];
-            s.add(acc[19]);
-            ab[0] = s.neg().to_affine();
-        }
+#pragma unroll 1
+        for (uint32_t l = 0; l < 2; l++)
+            if (serial || l == lane) ab[1 - l] = g1_sum_affine(l == 0 ? acc : acc + 18, l == 0 ? 18 : 2, l == 1);
         __syncwarp();
         Fq12 f;
         if (lane == 0) f = miller_loop(ab[0], vkp->X2);
-        else if (lane == 1) f1 = miller_loop(ab[1], g2_generator());
+        if (serial || lane == 1) f1 = miller_loop(ab[1], g2_generator());
         __syncwarp();
         if (lane == 0) valid[b] = final_exp(f12_mul(f, f1)).is_one() ? 1 : 0;
         __syncwarp();
@@ -279,8 +279,14 @@ extern "C" int32_t nzcb_plonk_verify_batch(nzcb_ctx* ctx, const nzcb_vkey* vk, c
     NZ_CUDA(ctx, cudaMemcpyAsync(d_proofs, proofs, B * sizeof(nzcb_proof), cudaMemcpyHostToDevice, ctx->stream));
     if (n_public)
         NZ_CUDA(ctx, cudaMemcpyAsync(d_pubs, public_le, B * (size_t)n_public * 32, cudaMemcpyHostToDevice, ctx->stream));
-    const uint32_t grid = (uint32_t)std::min<size_t>(B, (size_t)ctx->sm_count * 32);
-    NZ_LAUNCH(ctx, k_plonk_verify, grid, 32, 0, vk->d, d_proofs, d_pubs, n_public, (uint32_t)B, d_valid);
+    const char* serial = getenv("NZCB_VERIFY_SERIAL");
+    if (serial && serial[0] == '1') {
+        const uint32_t grid = (uint32_t)std::min<size_t>(B, (size_t)ctx->sm_count * 32);
+        NZ_LAUNCH(ctx, k_plonk_verify, grid, 1, 0, vk->d, d_proofs, d_pubs, n_public, (uint32_t)B, d_valid, 1);
+    } else {
+        const uint32_t grid = (uint32_t)std::min<size_t>(B, (size_t)ctx->sm_count * 32);
+        NZ_LAUNCH(ctx, k_plonk_verify, grid, 32, 0, vk->d, d_proofs, d_pubs, n_public, (uint32_t)B, d_valid, 0);
+    }
     NZ_CUDA(ctx, cudaMemcpyAsync(valid, d_valid, B * 4, cudaMemcpyDeviceToHost, ctx->stream));
     NZ_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     NZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

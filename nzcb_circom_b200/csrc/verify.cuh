@@ -42,7 +42,15 @@ NZ_HD void fr_to_be(const Fr& mont, uint8_t* be) {
         p[0] = (uint8_t)(c.v[i] >> 24), p[1] = (uint8_t)(c.v[i] >> 16), p[2] = (uint8_t)(c.v[i] >> 8), p[3] = (uint8_t)c.v[i];
     }
 }
-// hashToFr: the 256-bit big-endian digest reduced mod r (the Montgomery product by R^2 reduces any 256-bit input)
+// any 256-bit value -> [0, r): 2^256 < 6 r, five conditional subtractions.  The reduction has to come BEFORE the
+// Montgomery conversion: the device's carry-chain multiply drops carries its operands cannot produce when both are
+// below the modulus (fp.cuh), so an unreduced digest gives a wrong product there (the portable host multiply is
+// more forgiving, which is why the host check alone did not catch it).
+NZ_HD Fr fr_reduce_256(Fr x) {
+    for (int i = 0; i < 5; i++) x = Fr::reduce_once(x);
+    return x;
+}
+// hashToFr: the 256-bit big-endian digest reduced mod r
 NZ_HD Fr hash_finish_fr(KeccakHD& k) {
     uint8_t d[32];
     k.finish(d);
@@ -51,7 +59,7 @@ NZ_HD Fr hash_finish_fr(KeccakHD& k) {
         const uint8_t* p = d + 28 - 4 * i;
         x.v[i] = ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3];
     }
-    return x.to_mont();
+    return fr_reduce_256(x).to_mont();
 }
 
 // G1 point of the proof: x||y big-endian canonical, infinity = zeros; G1.isValid
@@ -90,7 +98,7 @@ NZ_HDN bool verify_prepare(const VkDev& vk, const uint8_t* proof, const uint8_t*
             const uint8_t* q = pubs + 32 * i + 4 * k;
             p.v[k] = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24);
         }
-        fr_to_be(p.to_mont(), buf);
+        fr_to_be(fr_reduce_256(p).to_mont(), buf);
         h.update(buf, 32);
     }
     h.update(proof, 192);
@@ -133,7 +141,7 @@ NZ_HDN bool verify_prepare(const VkDev& vk, const uint8_t* proof, const uint8_t*
                 const uint8_t* q = pubs + 32 * i + 4 * k;
                 p.v[k] = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24);
             }
-            pl = pl - p.to_mont() * li;
+            pl = pl - fr_reduce_256(p).to_mont() * li;
         }
         wi = wi * vk.w;
     }
@@ -175,6 +183,15 @@ NZ_HDN G1XYZZ g1_mul_limbs(const G1Affine& P, const Fr& k) {
     return acc;
 }
 
+// sum of n XYZZ points as an affine point (negated on request)
+NZ_HDN G1Affine g1_sum_affine(const G1XYZZ* a, int n, bool negate) {
+    G1XYZZ s = a[0];
+#pragma unroll 1
+    for (int i = 1; i < n; i++) s.add(a[i]);
+    if (negate) s = s.neg();
+    return s.to_affine();
+}
+
 // the whole check on one thread (the kernel spreads the 20 scalar multiplications and the two Miller loops over
 // the lanes of a warp; the host check and the single-thread reference use this)
 NZ_HDN bool verify_serial(const VkDev& vk, const uint8_t* proof, const uint8_t* pubs, uint32_t n_pub) {
@@ -182,10 +199,11 @@ NZ_HDN bool verify_serial(const VkDev& vk, const uint8_t* proof, const uint8_t* 
     Fr sc[VERIFY_TERMS];
     if (!verify_prepare(vk, proof, pubs, n_pub, pts, sc)) return false;
     if (!g2_on_curve(vk.X2)) return false;
-    G1XYZZ b1 = G1XYZZ::inf(), a1 = G1XYZZ::inf();
-    for (int i = 0; i < 18; i++) b1.add(g1_mul_limbs(pts[i], sc[i]));
-    for (int i = 18; i < 20; i++) a1.add(g1_mul_limbs(pts[i], sc[i]));
-    const Fq12 f = f12_mul(miller_loop(a1.neg().to_affine(), vk.X2), miller_loop(b1.to_affine(), g2_generator()));
+    G1XYZZ acc[VERIFY_TERMS];
+#pragma unroll 1
+    for (int i = 0; i < VERIFY_TERMS; i++) acc[i] = g1_mul_limbs(pts[i], sc[i]);
+    const Fq12 f = f12_mul(miller_loop(g1_sum_affine(acc + 18, 2, true), vk.X2),
+                           miller_loop(g1_sum_affine(acc, 18, false), g2_generator()));
     return final_exp(f).is_one();
 }
 

@@ -258,6 +258,19 @@ class _Plonk:
         del obuf
         return out
 
+    def setup_ptau(self, r1cs, ptau, ctx=None):
+        """`snarkjs plonk setup circuit.r1cs pot.ptau circuit.zkey` with the .ptau file (bytes / path)"""
+        ctx = ctx or default_context()
+        r, p = _bytes_of(r1cs), _bytes_of(ptau)
+        rbuf, pbuf = as_cbuf(r), as_cbuf(p)
+        n = ctypes.c_size_t(0)
+        ctx.check(ctx.lib.nzcb_plonk_setup_ptau(ctx.h, rbuf, len(r), pbuf, len(p), None, ctypes.byref(n)))
+        out = bytearray(n.value)
+        obuf = (ctypes.c_uint8 * n.value).from_buffer(out)
+        ctx.check(ctx.lib.nzcb_plonk_setup_ptau(ctx.h, rbuf, len(r), pbuf, len(p), obuf, ctypes.byref(n)))
+        del obuf
+        return out
+
     def setup_info(self, r1cs, ctx=None):
         """(nGates, nAdditions, plonkNVars, power) of the R1CS -> PLONK expansion"""
         ctx = ctx or default_context()
@@ -374,6 +387,16 @@ class _Powersoftau:
         ctx.check(ctx.lib.nzcb_srs_g1(ctx.h, t, count, out))
         return bytes(out)
 
+
+    def info(self, ptau):
+        """header of a .ptau: {power, ceremonyPower, nTauG1, prepared}; raises ValueError on a malformed file"""
+        from ._lib import load
+
+        p = _bytes_of(ptau)
+        v = [ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint64(), ctypes.c_int32()]
+        if load().nzcb_ptau_info(as_cbuf(p), len(p), *[ctypes.byref(x) for x in v]) != 0:
+            raise ValueError("not a bn128 .ptau file")
+        return {"power": v[0].value, "ceremonyPower": v[1].value, "nTauG1": v[2].value, "prepared": bool(v[3].value)}
 
     def new_g2(self, tau, ctx=None):
         """[tau]G2 as 128 affine LEM bytes: the tauG2 point of the same insecure SRS, X_2 of the zkey header"""
