@@ -48,7 +48,7 @@ def test_setup_from_ptau_matches_the_oracle(ctx, ptau_file):
     from nzcb_circom_b200 import NzcbError
     from nzcb_circom_b200.snarkjs import plonk
 
-    r, _ = random_circuit(3, n_out=3, n_in=4, n_mul=20, public_inputs=2)
+    r, _ = random_circuit(3, n_out=2, n_in=4, n_mul=8, public_inputs=2)
     gates, _, _ = oplonk.r1cs_to_plonk(r)
     n = 1 << max(3, (len(gates) - 1).bit_length())
     assert n <= 1 << POWER
@@ -59,6 +59,6 @@ def test_setup_from_ptau_matches_the_oracle(ctx, ptau_file):
     # snarkjs' two refusals
     with pytest.raises(NzcbError, match="not prepared"):
         plonk.setup_ptau(write_r1cs(r), optau.write_ptau(TAU, POWER, prepared=False), ctx)
-    big, _ = random_circuit(5, n_out=1, n_in=3, n_mul=120)
+    big, _ = random_circuit(5, n_out=1, n_in=3, n_mul=30)
     with pytest.raises(NzcbError, match="circuit too big"):
         plonk.setup_ptau(write_r1cs(big), optau.write_ptau(TAU, 3), ctx)
