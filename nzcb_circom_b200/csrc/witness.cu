@@ -15,6 +15,7 @@
 // (none for bit wires); wire * wire takes two unless both fit 32 bits.  IsZero's inverse hint
 // hits a 2 x 1024-entry table for the |x| <= 1024 operands the CBOR selectors produce
 //  and falls back to a Fermat inverse otherwise.
+#include <stdlib.h>
 #include "common.cuh"
 #include <algorithm>
 #include <cuda_pipeline.h>
@@ -70,7 +71,10 @@ __device__ __forceinline__ void lc_term(const ProgView& pv, Fr& acc, uint32_t c,
     else acc = acc + wit_mul(pv.consts[c], v);  // Montgomery const x canonical wire = canonical
 }
 
+// CTA sizes: 384 threads (one CTA fills an SM's registers) gives the shortest single-pass latency; batches larger
+// than the SM count run 128-thread CTAs, three per SM, so that one pass's barrier waits overlap another's work
 constexpr uint32_t WIT_THREADS = 384;
+constexpr uint32_t WIT_THREADS_BATCH = 128;
 constexpr uint32_t REC_WORDS = 32;
 constexpr uint32_t REC_LONG = 0x100u;  // flag on word 0: the encoding does not fit a record, word 1 = its code offset
 
@@ -80,9 +84,10 @@ struct GlobalCode {
     const uint32_t* code;
     __device__ __forceinline__ uint32_t operator()(uint32_t p) const { return code[p]; }
 };
+template <uint32_t T>
 struct SmemCode {
     const uint32_t* base;  // &slot[0][thread] viewed as words
-    __device__ __forceinline__ uint32_t operator()(uint32_t k) const { return base[(k >> 2) * (WIT_THREADS * 4) + (k & 3)]; }
+    __device__ __forceinline__ uint32_t operator()(uint32_t k) const { return base[(k >> 2) * (T * 4) + (k & 3)]; }
 };
 
 // canonical value of  k + sum coef_i * w_i ;  advances p past the encoded LC   (one thread)
@@ -221,7 +226,8 @@ __device__ __forceinline__ bool exec_instr(const ProgView& pv, const RD& rd, Fr*
 // LIN / MUL / ASSERT whose whole encoding sits in this thread's shared-memory record: every wire the instruction
 // reads is requested before the first one is used, so the three LCs of a product cost one memory round trip, not
 // three.  (BITS / INV and anything longer go through exec_instr.)
-__device__ __forceinline__ bool exec_short(const ProgView& pv, const SmemCode& rd, Fr* __restrict__ W, uint32_t op) {
+template <class RD>
+__device__ __forceinline__ bool exec_short(const ProgView& pv, const RD& rd, Fr* __restrict__ W, uint32_t op) {
     const uint32_t base_a = (op == OP_ASSERT ? 1u : 2u) + 2u;  // first term word of LC A
     const uint32_t na = rd(base_a - 2), ci_a = rd(base_a - 1);
     uint32_t nb = 0, nc = 0, ci_b = 0xffffffffu, ci_c = 0xffffffffu;
@@ -270,9 +276,11 @@ __device__ __forceinline__ bool exec_short(const ProgView& pv, const SmemCode& r
 // the instruction a thread will execute in the NEXT level is copied asynchronously (cp.async) from the flat record
 // array into its shared-memory slot while the current level runs, so a level's critical path is wire loads,
 // arithmetic, store, barrier -- no instruction fetch.
-__global__ void __launch_bounds__(WIT_THREADS) k_witness(ProgView pv, const Fr* __restrict__ inputs, Fr* __restrict__ wires,
-                                                         int32_t* __restrict__ status, uint32_t B) {
-    extern __shared__ uint4 s_rec[];  // [2][8][WIT_THREADS]
+template <uint32_t T, uint32_t CTAS_PER_SM>
+__global__ void __launch_bounds__(T, CTAS_PER_SM) k_witness(ProgView pv, const Fr* __restrict__ inputs, Fr* __restrict__ wires,
+                                                            int32_t* __restrict__ status, uint32_t B) {
+    extern __shared__ uint4 s_rec[];  // [2][8][T]
+    constexpr uint32_t WIT_THREADS = T;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = WIT_THREADS / 32;
     const GlobalCode gcode{pv.code};
     auto slot = [&](uint32_t buf, uint32_t k8) { return s_rec + ((size_t)buf * 8 + k8) * WIT_THREADS + threadIdx.x; };
@@ -309,7 +317,7 @@ __global__ void __launch_bounds__(WIT_THREADS) k_witness(ProgView pv, const Fr* 
             uint32_t i = lo + nl + threadIdx.x;
             if (i < hi) {
                 __pipeline_wait_prior(1);  // everything but the copy just issued has landed: this level's record
-                const SmemCode scode{reinterpret_cast<const uint32_t*>(slot(buf, 0))};
+                const SmemCode<T> scode{reinterpret_cast<const uint32_t*>(slot(buf, 0))};
                 const uint32_t w0 = scode(0), op = w0 & 0xffu;
                 if (w0 & REC_LONG) failed |= exec_instr<false>(pv, gcode, W, scode(1), lane);
                 else if (op == OP_BITS || op == OP_INV || op == OP_BITSLC) failed |= exec_instr<false>(pv, scode, W, 0, lane);
@@ -515,13 +523,25 @@ int witness_dev(nzcb_ctx* ctx, const nzcb_circuit* c, const Fr* d_inputs, size_t
     pv.nlong = c->d_nlong; pv.code = c->d_code; pv.invtab = c->d_invtab; pv.rec = c->d_rec;
     pv.n_total = c->n_total; pv.n_out = c->n_out; pv.n_in = c->n_in; pv.n_levels = c->n_levels;
     NZ_CUDA(ctx, cudaMemsetAsync(d_status, 0, B * sizeof(int32_t), ctx->stream));
-    const uint32_t grid = (uint32_t)std::min<size_t>(B, (size_t)ctx->sm_count * 8);
     constexpr size_t smem = (size_t)2 * 8 * WIT_THREADS * sizeof(uint4);
+    constexpr size_t smem_b = (size_t)2 * 8 * WIT_THREADS_BATCH * sizeof(uint4);
     static const bool attr_set = [] {
-        return cudaFuncSetAttribute(k_witness, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess;
+        return cudaFuncSetAttribute(k_witness<WIT_THREADS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess &&
+               cudaFuncSetAttribute(k_witness<WIT_THREADS_BATCH, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b) == cudaSuccess;
     }();
     if (!attr_set) return ctx->fail(NZCB_E_CUDA, "witness: cannot reserve %zu bytes of shared memory", smem);
-    NZ_LAUNCH(ctx, k_witness, grid, WIT_THREADS, smem, pv, d_inputs, d_wires, d_status, (uint32_t)B);
+    static const int force = [] {
+        const char* e = getenv("NZCB_WITNESS_CTA");  // 384 / 128: pin one variant (measurements)
+        return e ? atoi(e) : 0;
+    }();
+    const bool batch = force ? force == (int)WIT_THREADS_BATCH : B > (size_t)ctx->sm_count;
+    if (batch) {
+        const uint32_t grid = (uint32_t)std::min<size_t>(B, (size_t)ctx->sm_count * 3);
+        NZ_LAUNCH(ctx, (k_witness<WIT_THREADS_BATCH, 3>), grid, WIT_THREADS_BATCH, smem_b, pv, d_inputs, d_wires, d_status, (uint32_t)B);
+    } else {
+        const uint32_t grid = (uint32_t)std::min<size_t>(B, (size_t)ctx->sm_count * 8);
+        NZ_LAUNCH(ctx, (k_witness<WIT_THREADS, 1>), grid, WIT_THREADS, smem, pv, d_inputs, d_wires, d_status, (uint32_t)B);
+    }
     return 0;
 }
 uint32_t circuit_n_total(const nzcb_circuit* c) { return c->n_total; }
