@@ -527,9 +527,7 @@ int witness_dev(nzcb_ctx* ctx, const nzcb_circuit* c, const Fr* d_inputs, size_t
     constexpr size_t smem_b = (size_t)2 * 8 * WIT_THREADS_BATCH * sizeof(uint4);
     static const bool attr_set = [] {
         return cudaFuncSetAttribute(k_witness<WIT_THREADS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess &&
-               cudaFuncSetAttribute(k_witness<WIT_THREADS_BATCH, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b) == cudaSuccess &&
-               cudaFuncSetAttribute(k_witness<WIT_THREADS_BATCH, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b) == cudaSuccess &&
-               cudaFuncSetAttribute(k_witness<WIT_THREADS_BATCH, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b) == cudaSuccess;
+               cudaFuncSetAttribute(k_witness<WIT_THREADS_BATCH, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b) == cudaSuccess;
     }();
     if (!attr_set) return ctx->fail(NZCB_E_CUDA, "witness: cannot reserve %zu bytes of shared memory", smem);
     static const int force = [] {
@@ -537,13 +535,7 @@ int witness_dev(nzcb_ctx* ctx, const nzcb_circuit* c, const Fr* d_inputs, size_t
         return e ? atoi(e) : 0;
     }();
     const bool batch = force ? force != (int)WIT_THREADS : B > (size_t)ctx->sm_count;
-    if (force == 1284) {
-        const uint32_t grid = (uint32_t)std::min<size_t>(B, (size_t)ctx->sm_count * 4);
-        NZ_LAUNCH(ctx, (k_witness<WIT_THREADS_BATCH, 4>), grid, WIT_THREADS_BATCH, smem_b, pv, d_inputs, d_wires, d_status, (uint32_t)B);
-    } else if (force == 1285) {
-        const uint32_t grid = (uint32_t)std::min<size_t>(B, (size_t)ctx->sm_count * 5);
-        NZ_LAUNCH(ctx, (k_witness<WIT_THREADS_BATCH, 5>), grid, WIT_THREADS_BATCH, smem_b, pv, d_inputs, d_wires, d_status, (uint32_t)B);
-    } else if (batch) {
+    if (batch) {
         const uint32_t grid = (uint32_t)std::min<size_t>(B, (size_t)ctx->sm_count * 3);
         NZ_LAUNCH(ctx, (k_witness<WIT_THREADS_BATCH, 3>), grid, WIT_THREADS_BATCH, smem_b, pv, d_inputs, d_wires, d_status, (uint32_t)B);
     } else {

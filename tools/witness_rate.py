@@ -8,7 +8,7 @@ base=[]
 for i in range(64):
     p = H.synth_pass(i)
     base.append(cir.compiled.flatten_input(H.nzcp_input(p["toBeSigned"], 351, p["data"])))
-for B in (1, 148, 444, 2048, 8192):
+for B in [int(x) for x in os.environ.get("WR_B", "1,148,444,2048,8192").split(",")]:
     inputs=[base[i%64] for i in range(B)]
     for it in range(2):
         raw, st = cir.calculateWitnessBatch(inputs, True, c, want_witness=False)
