@@ -44,17 +44,33 @@ __global__ void __launch_bounds__(32) k_plonk_verify(const VkDev* __restrict__ v
             __syncwarp();
             continue;
         }
+        // every phase has ONE call site that all participating lanes reach in the same iteration (lanes that took
+        // different call sites, or the same one in different iterations, would run one after the other); the serial
+        // mode walks the lane index on one thread instead
+        const uint32_t n_it20 = serial ? VERIFY_TERMS : 1, n_it2 = serial ? 2 : 1;
 #pragma unroll 1
-        for (uint32_t l = 0; l < VERIFY_TERMS; l++)
-            if (serial || l == lane) acc[l] = g1_mul_limbs(pts[l], sc[l]);
+        for (uint32_t it = 0; it < n_it20; it++) {
+            const uint32_t l = serial ? it : lane;
+            if (l < VERIFY_TERMS) acc[l] = g1_mul_limbs(pts[l], sc[l]);
+        }
         __syncwarp();
 #pragma unroll 1
-        for (uint32_t l = 0; l < 2; l++)
-            if (serial || l == lane) ab[1 - l] = g1_sum_affine(l == 0 ? acc : acc + 18, l == 0 ? 18 : 2, l == 1);
+        for (uint32_t it = 0; it < n_it2; it++) {
+            const uint32_t l = serial ? it : lane;
+            if (l < 2) ab[1 - l] = g1_sum_affine(l == 0 ? acc : acc + 18, l == 0 ? 18 : 2, l == 1);
+        }
         __syncwarp();
         Fq12 f;
-        if (lane == 0) f = miller_loop(ab[0], vkp->X2);
-        if (serial || lane == 1) f1 = miller_loop(ab[1], g2_generator());
+#pragma unroll 1
+        for (uint32_t it = 0; it < n_it2; it++) {
+            const uint32_t l = serial ? it : lane;
+            if (l < 2) {
+                const G2Affine q = l == 0 ? vkp->X2 : g2_generator();
+                const Fq12 r = miller_loop(ab[l], q);
+                if (l == 0) f = r;
+                else f1 = r;
+            }
+        }
         __syncwarp();
         if (lane == 0) valid[b] = final_exp(f12_mul(f, f1)).is_one() ? 1 : 0;
         __syncwarp();
