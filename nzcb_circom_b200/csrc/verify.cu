@@ -3,10 +3,11 @@
 // from verification_key.json (`snarkjs zkey export verificationkey`, /root/reference/Makefile:56,61), [tau]_2 for the
 // synthetic SRS, and `snarkjs zkey export soliditycalldata`'s text for a proof.
 //
-// One warp per proof.  Lane 0 checks the proof's form, replays the Fiat-Shamir transcript (Keccak-256) and derives
-// the twenty scalars; lanes 0..19 each do one G1 scalar multiplication; lanes 0 and 1 add up B1 and A1 and run one
-// Miller loop each; lane 0 multiplies the two and does the final exponentiation.  A verification is latency-bound
-// (a chain of ~50 k dependent Fq multiplications), so throughput comes from the batch: B proofs = B warps.
+// One warp per proof in the latency form: lane 0 checks the proof's form, replays the Fiat-Shamir transcript
+// (Keccak-256) and derives the twenty scalars; lanes 0..19 each do one G1 scalar multiplication; lanes 0 and 1 add up
+// B1 and A1 and run one Miller loop each; lane 0 multiplies the two and does the final exponentiation.  A
+// verification is latency-bound (a chain of ~25 k dependent Fq multiplications), so throughput comes from the batch:
+// B proofs = B warps, and once the GPU's warp slots are full, up to 16 proofs per warp (see k_plonk_verify).
 #include <stdlib.h>
 #include "common.cuh"
 #include "verify.cuh"
@@ -21,58 +22,71 @@ struct nzcb_vkey {
 
 namespace {
 
-// serial = 0: one warp per proof, the scalar multiplications and the two Miller loops spread over the lanes.
-// serial = 1 (NZCB_VERIFY_SERIAL=1): the same steps on one thread per proof (blockDim 1) -- a cross-check of the
-// lane choreography.
+// One warp verifies G proofs at a time (G = 1, 2, 4, 8 or 16, chosen by the host from the batch size).  Every phase
+// has ONE call site that all participating lanes reach together, so the lanes run side by side:
+//   A  lanes < G        : form checks, transcript, scalars of "their" proof            (verify_prepare)
+//   B  20 G work items  : one G1 scalar multiplication each, 32 at a time              (g1_mul_limbs)
+//   C  lanes < 2 G      : B1 and -A1 of proof lane/2                                   (g1_sum_affine)
+//   D  lanes < 2 G      : one Miller loop each                                         (miller_loop)
+//   E  lanes < G        : product of the two loops, final exponentiation, verdict     (final_exp)
+// G = 1 is the latency form (one proof spread over a warp: 20 lanes in B, 2 in D); G = 16 fills the lanes in every
+// phase but A and E (half) -- the throughput form for large batches.  serial = 1 (NZCB_VERIFY_SERIAL=1, blockDim 1)
+// walks the lane index on one thread: a cross-check of the lane choreography.
+constexpr uint32_t VERIFY_GMAX = 16;
+struct VerifySmem {  // per proof of the group
+    G1Affine pts[VERIFY_TERMS];
+    Fr sc[VERIFY_TERMS];
+    G1XYZZ acc[VERIFY_TERMS];
+    G1Affine ab[2];
+    Fq12 fm[2];
+    int ok, pad[7];
+};
+
 __global__ void __launch_bounds__(32) k_plonk_verify(const VkDev* __restrict__ vkp, const uint8_t* __restrict__ proofs,
                                                      const uint8_t* __restrict__ pubs, uint32_t n_pub, uint32_t B,
-                                                     int32_t* __restrict__ valid, int serial) {
-    __shared__ G1Affine pts[VERIFY_TERMS];
-    __shared__ Fr sc[VERIFY_TERMS];
-    __shared__ G1XYZZ acc[VERIFY_TERMS];
-    __shared__ G1Affine ab[2];
-    __shared__ Fq12 f1;
-    __shared__ int ok;
-    const uint32_t lane = threadIdx.x;
-    for (uint32_t b = blockIdx.x; b < B; b += gridDim.x) {
-        if (lane == 0)
-            ok = verify_prepare(*vkp, proofs + (size_t)b * sizeof(nzcb_proof), pubs + (size_t)b * n_pub * 32, n_pub, pts, sc) &&
-                 g2_on_curve(vkp->X2);
-        __syncwarp();
-        if (!ok) {
-            if (lane == 0) valid[b] = 0;
-            __syncwarp();
-            continue;
-        }
-        // every phase has ONE call site that all participating lanes reach in the same iteration (lanes that took
-        // different call sites, or the same one in different iterations, would run one after the other); the serial
-        // mode walks the lane index on one thread instead
-        const uint32_t n_it20 = serial ? VERIFY_TERMS : 1, n_it2 = serial ? 2 : 1;
+                                                     int32_t* __restrict__ valid, int serial, uint32_t G) {
+    extern __shared__ uint4 verify_smem_raw[];
+    VerifySmem* sm = reinterpret_cast<VerifySmem*>(verify_smem_raw);
+    const uint32_t n_groups = (B + G - 1) / G;
+    const uint32_t width = serial ? 1u : 32u;  // lanes that walk the work items of a phase
+    for (uint32_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+        const uint32_t b0 = grp * G, g_here = min(G, B - b0);
+        // A
 #pragma unroll 1
-        for (uint32_t it = 0; it < n_it20; it++) {
-            const uint32_t l = serial ? it : lane;
-            if (l < VERIFY_TERMS) acc[l] = g1_mul_limbs(pts[l], sc[l]);
+        for (uint32_t w = threadIdx.x; w < g_here; w += width) {
+            const uint32_t b = b0 + w;
+            sm[w].ok = verify_prepare(*vkp, proofs + (size_t)b * sizeof(nzcb_proof), pubs + (size_t)b * n_pub * 32, n_pub,
+                                      sm[w].pts, sm[w].sc) && g2_on_curve(vkp->X2);
         }
         __syncwarp();
+        // B
 #pragma unroll 1
-        for (uint32_t it = 0; it < n_it2; it++) {
-            const uint32_t l = serial ? it : lane;
-            if (l < 2) ab[1 - l] = g1_sum_affine(l == 0 ? acc : acc + 18, l == 0 ? 18 : 2, l == 1);
+        for (uint32_t w = threadIdx.x; w < g_here * VERIFY_TERMS; w += width) {
+            const uint32_t p = w / VERIFY_TERMS, t = w % VERIFY_TERMS;
+            if (sm[p].ok) sm[p].acc[t] = g1_mul_limbs(sm[p].pts[t], sm[p].sc[t]);
         }
         __syncwarp();
-        Fq12 f;
+        // C
 #pragma unroll 1
-        for (uint32_t it = 0; it < n_it2; it++) {
-            const uint32_t l = serial ? it : lane;
-            if (l < 2) {
+        for (uint32_t w = threadIdx.x; w < g_here * 2; w += width) {
+            const uint32_t p = w >> 1, l = w & 1;
+            if (sm[p].ok) sm[p].ab[1 - l] = g1_sum_affine(l == 0 ? sm[p].acc : sm[p].acc + 18, l == 0 ? 18 : 2, l == 1);
+        }
+        __syncwarp();
+        // D
+#pragma unroll 1
+        for (uint32_t w = threadIdx.x; w < g_here * 2; w += width) {
+            const uint32_t p = w >> 1, l = w & 1;
+            if (sm[p].ok) {
                 const G2Affine q = l == 0 ? vkp->X2 : g2_generator();
-                const Fq12 r = miller_loop(ab[l], q);
-                if (l == 0) f = r;
-                else f1 = r;
+                sm[p].fm[l] = miller_loop(sm[p].ab[l], q);
             }
         }
         __syncwarp();
-        if (lane == 0) valid[b] = final_exp(f12_mul(f, f1)).is_one() ? 1 : 0;
+        // E
+#pragma unroll 1
+        for (uint32_t w = threadIdx.x; w < g_here; w += width)
+            valid[b0 + w] = sm[w].ok && final_exp(f12_mul(sm[w].fm[0], sm[w].fm[1])).is_one() ? 1 : 0;
         __syncwarp();
     }
 }
@@ -295,13 +309,29 @@ extern "C" int32_t nzcb_plonk_verify_batch(nzcb_ctx* ctx, const nzcb_vkey* vk, c
     NZ_CUDA(ctx, cudaMemcpyAsync(d_proofs, proofs, B * sizeof(nzcb_proof), cudaMemcpyHostToDevice, ctx->stream));
     if (n_public)
         NZ_CUDA(ctx, cudaMemcpyAsync(d_pubs, public_le, B * (size_t)n_public * 32, cudaMemcpyHostToDevice, ctx->stream));
-    const char* serial = getenv("NZCB_VERIFY_SERIAL");
-    if (serial && serial[0] == '1') {
-        const uint32_t grid = (uint32_t)std::min<size_t>(B, (size_t)ctx->sm_count * 32);
-        NZ_LAUNCH(ctx, k_plonk_verify, grid, 1, 0, vk->d, d_proofs, d_pubs, n_public, (uint32_t)B, d_valid, 1);
-    } else {
-        const uint32_t grid = (uint32_t)std::min<size_t>(B, (size_t)ctx->sm_count * 32);
-        NZ_LAUNCH(ctx, k_plonk_verify, grid, 32, 0, vk->d, d_proofs, d_pubs, n_public, (uint32_t)B, d_valid, 0);
+    const char* e_serial = getenv("NZCB_VERIFY_SERIAL");
+    const char* e_group = getenv("NZCB_VERIFY_GROUP");  // proofs per warp: 1, 2, 4, 8, 16 (default: from the batch size)
+    const int serial = e_serial && e_serial[0] == '1';
+    // two warps per SM run at nearly the single-proof latency (a third already slows all of them: 1,024 warps of
+    // one proof took 86 ms, 256 warps of sixteen 93 ms); beyond that, pack more proofs into a warp
+    uint32_t G = 1;
+    const size_t slots = (size_t)ctx->sm_count * 2;
+    while (G < VERIFY_GMAX && B > slots * G) G *= 2;
+    if (e_group) {
+        const int g = atoi(e_group);
+        if (g == 1 || g == 2 || g == 4 || g == 8 || g == 16) G = (uint32_t)g;
+    }
+    if (serial) G = 1;
+    static const bool attr_set = [] {
+        return cudaFuncSetAttribute(k_plonk_verify, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)(VERIFY_GMAX * sizeof(VerifySmem))) == cudaSuccess;
+    }();
+    if (!attr_set) return ctx->fail(NZCB_E_CUDA, "verify: cannot reserve %zu bytes of shared memory", VERIFY_GMAX * sizeof(VerifySmem));
+    {
+        const size_t n_groups = (B + G - 1) / G;
+        const uint32_t grid = (uint32_t)std::min<size_t>(n_groups, (size_t)ctx->sm_count * 32);
+        NZ_LAUNCH(ctx, k_plonk_verify, grid, serial ? 1 : 32, G * sizeof(VerifySmem), vk->d, d_proofs, d_pubs, n_public,
+                  (uint32_t)B, d_valid, serial, G);
     }
     NZ_CUDA(ctx, cudaMemcpyAsync(valid, d_valid, B * 4, cudaMemcpyDeviceToHost, ctx->stream));
     NZ_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));

@@ -185,6 +185,12 @@ def test_gpu_verify_matches_the_oracle(ctx, name):
     muts = _mutations(proof, pub, random.Random(2))
     got = plonk.verify_batch(vkey, [m[2] for m in muts], [m[1] for m in muts], ctx)
     assert got == [m[3] for m in muts], [m[0] for m in muts]
+    for env, val in (("NZCB_VERIFY_GROUP", "16"), ("NZCB_VERIFY_GROUP", "8"), ("NZCB_VERIFY_SERIAL", "1")):
+        os.environ[env] = val                                # the packed and the one-thread forms agree
+        try:
+            assert plonk.verify_batch(vkey, [m[2] for m in muts], [m[1] for m in muts], ctx) == got, (env, val)
+        finally:
+            del os.environ[env]
     assert got == [op.verify(vk, m[2], op.proof_from_bytes(m[1])) for m in muts]
     assert plonk.verify(vkey, pub, json.loads(fx["proof_json"]), ctx) is True      # the snarkjs call shape
     assert plonk.verify_batch(vkey, [pub + [0]], [proof], ctx) == [False]         # nPublic mismatch
@@ -221,5 +227,12 @@ def test_gpu_nzcp_live_proofs_verify_on_the_device(nzcp_live_prover):
         publics.append(pubs[i % 2])
         want.append(i % 2 == 0)
     assert plonk.verify_batch(vkey, publics, proofs, pr.ctx) == want
+    for group in ("16", "4", "2"):                             # several proofs per warp: the large-batch form
+        os.environ["NZCB_VERIFY_GROUP"] = group
+        try:
+            assert plonk.verify_batch(vkey, publics[:1000], proofs[:1000], pr.ctx) == want[:1000], group
+            assert plonk.verify_batch(vkey, publics[:3], proofs[:3], pr.ctx) == want[:3], group   # a ragged last group
+        finally:
+            del os.environ["NZCB_VERIFY_GROUP"]
     print("verify batch of 1024: %.1f ms on the device" % pr.ctx.last_device_ms)
     vkey.close()

@@ -39,7 +39,13 @@ vkj["X_2"] = [[co[0], co[1]], [co[2], co[3]], ["1", "0"]]
 vk = VKey(vkj, c)
 proof = bytes.fromhex(fx["proof_hex"])
 pub = [int(x) for x in fx["public_signals"]]
-for n in (1, 256, 4096):
+for n in (1, 256, 1024, 4096, 32768):
     for _ in range(2):
         ok = plonk.verify_batch(vk, [pub] * n, [proof] * n, c)
     print(f"verify {n} proofs: {c.last_device_ms:.2f} ms ({n / c.last_device_ms * 1e3:.0f} proofs/s), all valid={all(ok)}")
+for g in ("1", "4", "16"):
+    os.environ["NZCB_VERIFY_GROUP"] = g
+    n = 32768 if g != "1" else 4096
+    for _ in range(2):
+        ok = plonk.verify_batch(vk, [pub] * n, [proof] * n, c)
+    print(f"verify {n} proofs, {g} per warp: {c.last_device_ms:.2f} ms ({n / c.last_device_ms * 1e3:.0f} proofs/s), all valid={all(ok)}")
