@@ -33,14 +33,23 @@ namespace {
 // phase but A and E (half) -- the throughput form for large batches.  serial = 1 (NZCB_VERIFY_SERIAL=1, blockDim 1)
 // walks the lane index on one thread: a cross-check of the lane choreography.
 constexpr uint32_t VERIFY_GMAX = 16;
-struct VerifySmem {  // per proof of the group
-    G1Affine pts[VERIFY_TERMS];
-    Fr sc[VERIFY_TERMS];
-    G1XYZZ acc[VERIFY_TERMS];
-    G1Affine ab[2];
-    Fq12 fm[2];
+// Shared memory per proof of the group, 2.6 KB: a work item's point and scalar (96 B, phase A -> B) are overwritten by
+// its product (128 B, phase B -> C); the two summed points and then the two Miller values (phase C -> D -> E) reuse
+// the items' space once the products are dead.  16 proofs = 41.5 KB, so five groups fit an SM.
+struct VerifyItem {
+    union {
+        struct {
+            G1Affine pt;
+            Fr sc;
+        } in;
+        G1XYZZ acc;
+    };
+};
+struct VerifySmem {
+    VerifyItem item[VERIFY_TERMS];
     int ok, pad[7];
 };
+static_assert(sizeof(VerifyItem) == 128 && 2 * sizeof(Fq12) + 2 * sizeof(G1Affine) <= 8 * sizeof(VerifyItem), "layout");
 
 __global__ void __launch_bounds__(32) k_plonk_verify(const VkDev* __restrict__ vkp, const uint8_t* __restrict__ proofs,
                                                      const uint8_t* __restrict__ pubs, uint32_t n_pub, uint32_t B,
@@ -49,44 +58,74 @@ __global__ void __launch_bounds__(32) k_plonk_verify(const VkDev* __restrict__ v
     VerifySmem* sm = reinterpret_cast<VerifySmem*>(verify_smem_raw);
     const uint32_t n_groups = (B + G - 1) / G;
     const uint32_t width = serial ? 1u : 32u;  // lanes that walk the work items of a phase
+    G1Affine serial_first = G1Affine::inf();
     for (uint32_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
         const uint32_t b0 = grp * G, g_here = min(G, B - b0);
-        // A
+        // A  (verify_prepare fills plain arrays: staged in this lane's stack, then scattered into the items)
 #pragma unroll 1
         for (uint32_t w = threadIdx.x; w < g_here; w += width) {
             const uint32_t b = b0 + w;
-            sm[w].ok = verify_prepare(*vkp, proofs + (size_t)b * sizeof(nzcb_proof), pubs + (size_t)b * n_pub * 32, n_pub,
-                                      sm[w].pts, sm[w].sc) && g2_on_curve(vkp->X2);
+            G1Affine pts[VERIFY_TERMS];
+            Fr sc[VERIFY_TERMS];
+            const bool ok = verify_prepare(*vkp, proofs + (size_t)b * sizeof(nzcb_proof), pubs + (size_t)b * n_pub * 32, n_pub,
+                                           pts, sc) && g2_on_curve(vkp->X2);
+            sm[w].ok = ok;
+            if (ok)
+                for (int t = 0; t < VERIFY_TERMS; t++) {
+                    sm[w].item[t].in.pt = pts[t];
+                    sm[w].item[t].in.sc = sc[t];
+                }
         }
         __syncwarp();
         // B
 #pragma unroll 1
         for (uint32_t w = threadIdx.x; w < g_here * VERIFY_TERMS; w += width) {
             const uint32_t p = w / VERIFY_TERMS, t = w % VERIFY_TERMS;
-            if (sm[p].ok) sm[p].acc[t] = g1_mul_limbs(sm[p].pts[t], sm[p].sc[t]);
+            if (sm[p].ok) {
+                const G1Affine P = sm[p].item[t].in.pt;
+                const Fr k = sm[p].item[t].in.sc;
+                sm[p].item[t].acc = g1_mul_limbs(P, k);
+            }
         }
         __syncwarp();
-        // C
+        // C: both sums of a proof are taken before either is stored (they overwrite products 0 and 1)
+        G1Affine sum = G1Affine::inf();
 #pragma unroll 1
         for (uint32_t w = threadIdx.x; w < g_here * 2; w += width) {
             const uint32_t p = w >> 1, l = w & 1;
-            if (sm[p].ok) sm[p].ab[1 - l] = g1_sum_affine(l == 0 ? sm[p].acc : sm[p].acc + 18, l == 0 ? 18 : 2, l == 1);
+            if (sm[p].ok) sum = g1_sum_affine(l == 0 ? &sm[p].item[0].acc : &sm[p].item[18].acc, l == 0 ? 18 : 2, l == 1);
+            if (serial) {  // one thread: keep the first sum in a register-resident copy until the second is done
+                if (l == 0) serial_first = sum;
+                else if (sm[p].ok) {
+                    G1Affine* ab = reinterpret_cast<G1Affine*>(&sm[p].item[0]);
+                    ab[1] = serial_first;
+                    ab[0] = sum;
+                }
+            }
         }
         __syncwarp();
-        // D
+        if (!serial) {
+            const uint32_t w = threadIdx.x;
+            if (w < g_here * 2 && sm[w >> 1].ok) reinterpret_cast<G1Affine*>(&sm[w >> 1].item[0])[1 - (w & 1)] = sum;
+        }
+        __syncwarp();
+        // D: the Miller values go to items 2..7 (ab lives in item 0)
 #pragma unroll 1
         for (uint32_t w = threadIdx.x; w < g_here * 2; w += width) {
             const uint32_t p = w >> 1, l = w & 1;
             if (sm[p].ok) {
                 const G2Affine q = l == 0 ? vkp->X2 : g2_generator();
-                sm[p].fm[l] = miller_loop(sm[p].ab[l], q);
+                const G1Affine a = reinterpret_cast<const G1Affine*>(&sm[p].item[0])[l];
+                reinterpret_cast<Fq12*>(&sm[p].item[2])[l] = miller_loop(a, q);
             }
         }
         __syncwarp();
         // E
 #pragma unroll 1
-        for (uint32_t w = threadIdx.x; w < g_here; w += width)
-            valid[b0 + w] = sm[w].ok && final_exp(f12_mul(sm[w].fm[0], sm[w].fm[1])).is_one() ? 1 : 0;
+        for (uint32_t w = threadIdx.x; w < g_here; w += width) {
+            const Fq12* fm = reinterpret_cast<const Fq12*>(&sm[w].item[2]);
+            valid[b0 + w] = sm[w].ok && final_exp(f12_mul(fm[0], fm[1])).is_one() ? 1 : 0;
+        }
         __syncwarp();
     }
 }
