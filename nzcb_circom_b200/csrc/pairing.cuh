@@ -13,6 +13,7 @@
 #include "g1.cuh"
 #include "pairing_consts.cuh"
 
+// NZ_HDN routines have external linkage under nvcc: include this header (and verify.cuh) from ONE .cu only.
 #ifdef __CUDACC__
 #define NZ_HDN __host__ __device__ __noinline__
 #else
