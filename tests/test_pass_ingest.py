@@ -84,6 +84,59 @@ def test_kernel_header_matches_the_oracle_on_the_host(fc):
     assert n_ok >= 80
 
 
+def test_kernel_header_fuzz_against_the_oracle(fc):
+    """random COSE-like byte strings (every length form of CBOR heads, the empty-object variants of data[1], byte
+    corruption, truncation, ragged base32 tails, several maxLen): header and oracle agree on every case"""
+    from tests.pass_cases import b32encode
+
+    rng = random.Random(2024)
+    heads = [b"\xd2\x84", b"\xd2\x98\x04", b"\xd2\x99\x00\x04", b"\xd2\x9a\x00\x00\x00\x04", b"\xd2\x9b" + bytes(7) + b"\x04",
+             b"\xd2\x83", b"\xd1\x84", b"\xd2\xa4", b"\xd2\x9f", b"\xd2\x44"]
+    unprots = [b"\xa0", b"\x80", b"\x40", b"\x60", b"\xb8\x00", b"\x98\x00", b"\x58\x00", b"\xa1\x01\x02", b"\xf6", b"\x00",
+               b"\x20", b"\xba\x00\x00\x00\x00", b"\xbb" + bytes(8), b"\x5b" + bytes(8), b"\xc0\xa0"]
+
+    def bstr_any(x):
+        n, k = len(x), rng.randrange(5)
+        if k == 0 and n <= 23:
+            return bytes([0x40 + n]) + x
+        if k <= 1 and n < 256:
+            return bytes([0x58, n]) + x
+        if k <= 2:
+            return bytes([0x59, n >> 8, n & 255]) + x
+        if k == 3:
+            return bytes([0x5A]) + n.to_bytes(4, "big") + x
+        return bytes([0x5B]) + n.to_bytes(8, "big") + x
+
+    accepted = 0
+    for it in range(1500):
+        prot = bytes(rng.randrange(256) for _ in range(rng.choice([0, 1, 10, 13, 23, 24, 30])))
+        pay = bytes(rng.randrange(256) for _ in range(rng.choice([0, 5, 200, 255, 256, 300, 340, 700])))
+        sig = bytes(rng.randrange(256) for _ in range(rng.choice([0, 64, 10])))
+        raw = rng.choice(heads) + bstr_any(prot) + rng.choice(unprots) + bstr_any(pay) + bstr_any(sig)
+        r = rng.random()
+        if r < 0.3:
+            raw = bytearray(raw)
+            for _ in range(rng.randrange(1, 4)):
+                raw[rng.randrange(len(raw))] = rng.randrange(256)
+            raw = bytes(raw)
+        elif r < 0.4:
+            raw = raw[:rng.randrange(len(raw))]
+        uri = rng.choice(["NZCP:/1/", "12345678", "NZCP:/2/"]) + b32encode(raw)
+        if rng.random() < 0.1:
+            uri = uri[:-1]
+        max_len = rng.choice([314, 351, 64, 1024])
+        d20 = bytes(rng.randrange(256) for _ in range(20))
+        st, fitted, ln, inputs = pi.ingest(uri, max_len, d20)
+        ub = uri.encode("latin-1")
+        tbs = ctypes.create_string_buffer(max_len)
+        tl = ctypes.c_uint32()
+        inp = (ctypes.c_uint32 * (8 * max_len + 161))()
+        rc = fc.fc_ingest(ub + bytes(16), len(ub), d20, max_len, tbs, ctypes.byref(tl), inp)
+        assert (rc, tbs.raw, tl.value) == (st, fitted, ln) and list(inp) == inputs, (it, raw[:24].hex())
+        accepted += st == 0
+    assert 200 < accepted < 1300
+
+
 # ---------------------------------------------------------------- GPU
 def _check_batch(ctx, uris, max_len, datas):
     from nzcb_circom_b200.pass_ingest import toBeSignedBatch
