@@ -61,3 +61,19 @@ def test_proof_to_json_needs_no_gpu():
     buf = ctypes.create_string_buffer(n.value)
     assert lib.nzcb_proof_to_json(ctypes.byref(p), buf, ctypes.byref(n)) == 0
     assert b'"protocol": "plonk"' in buf.value and b'"curve": "bn128"' in buf.value
+
+
+def test_napi_shim_type_checks_against_the_header():
+    """integration/nzcb_napi.c (the binding a maintainer of the reference adds; Node is absent here) compiles against
+    include/nzcb.h and a stub of the N-API declarations it uses, and calls only functions the header declares"""
+    import shutil
+    import subprocess
+    import tempfile
+
+    with tempfile.TemporaryDirectory() as d:
+        shutil.copy(os.path.join(ROOT, "tests", "hostcheck", "node_api_stub.h"), os.path.join(d, "node_api.h"))
+        subprocess.run(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-I", d, "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "integration", "nzcb_napi.c")], check=True)
+    with open(os.path.join(ROOT, "integration", "nzcb_napi.c")) as f:
+        used = set(re.findall(r"\b(nzcb_[a-z0-9_]+)\s*\(", re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)))
+    assert used and used <= set(_declared()) | {"nzcb_napi_register_stub"}, used - set(_declared())
