@@ -15,4 +15,11 @@ outputs of the reference's own tests (test/nzcp.js:62-68, test/utils.js:17,
 test/cbor.js, test/quinSelector.js), Keccak/SHA known-answer tests, and the
 algebraic self-consistency of prover vs. an independently written verifier
 plus a known-trapdoor KZG check.
+
+Modules: bn254 / ntt / keccak (field, curve, transform, transcript hash), binfile (iden3 file formats), plonk (setup,
+prove, verify), witness_vm (the witness program interpreter), c/ (the same path in C with OpenMP: the CPU baseline),
+pairing (BN254 optimal ate pairing: pinned by bilinearity, non-degeneracy and order r, and by agreeing with the
+known-trapdoor form of plonk.verify), pass_ingest (test/helpers/nzcp.js with JavaScript's number semantics: pinned
+by the reference's EXAMPLE_PASS_URI -> ToBeSigned -> SHA-256 of test/utils.js:17), ptau (writer of a small
+known-trapdoor .ptau for the reader's tests: format recalled, unpinned).
 """
