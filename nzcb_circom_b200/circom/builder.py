@@ -16,6 +16,7 @@ and only quadratic assignments, hints, inputs and outputs become wires.  Wire
 order is circom's convention where it is observable: 1, outputs, inputs in
 declaration order (test/nzcp.js:44, test/cbor.js:191-193), then internals.
 """
+import os
 import struct
 
 R = 0x30644e72e131a029b85045b68181585d2833e84879b9709143e1f593f0000001
@@ -155,6 +156,7 @@ class Circuit:
         self.constraints = []     # (A, B, C) dicts
         self.prog = []            # instruction tuples
         self.output_assigned = set()
+        self.drop_implied = os.environ.get("NZCB_WITNESS_DROP_IMPLIED") == "1"  # see assert_zero
 
     # ---- declaration -------------------------------------------------
     @staticmethod
@@ -282,8 +284,12 @@ class Circuit:
         return LC({w: 1})
 
     # ---- constraints ---------------------------------------------------
-    def assert_zero(self, x):
-        """x === 0 (constraint + run-time assert, circom_runtime error 4 "Assert Failed")"""
+    def assert_zero(self, x, implied=False):
+        """x === 0 (constraint + run-time assert, circom_runtime error 4 "Assert Failed").
+        implied=True marks a check that holds by construction of the witness program itself -- the booleanity of
+        bits a decomposition instruction has just written, `in * out === 0` of IsZero after its inverse hint: it
+        stays a constraint of the R1CS, and with NZCB_WITNESS_DROP_IMPLIED=1 it costs no run-time instruction (it
+        can never fire).  Off by default until the slimmer program has been through the GPU parity suite."""
         if isinstance(x, Quad) and not (x.a.is_const() or x.b.is_const()):
             a, b, c = x.a, x.b, -x.c
         else:
@@ -295,7 +301,8 @@ class Circuit:
                     raise ValueError("constraint is never satisfiable")
                 return
             a, b, c = LC(), LC(), x
-        self.prog.append((OP_ASSERT, a, b, c))
+        if not (implied and self.drop_implied):
+            self.prog.append((OP_ASSERT, a, b, c))
         self.constraints.append((_terms(a), _terms(b), _terms(c)))
 
     def assert_eq(self, x, y):

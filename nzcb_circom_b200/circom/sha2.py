@@ -99,7 +99,7 @@ def _binsum(c: Circuit, n, ops):
     bits = c.hint_bits(lin, nout)
     acc = LC()
     for i, b in enumerate(bits):
-        c.assert_zero(b * (b - 1))
+        c.assert_zero(b * (b - 1), implied=True)  # b was just written by the decomposition
         acc = acc + b * (1 << i)
     c.assert_eq(acc, lin)
     return bits[:n]

@@ -134,27 +134,29 @@ def compile_circuit(name, use_cache=True):
     key = _ALIAS.get(key, key)
     if key not in MAINS:
         raise FileNotFoundError(f"no main component known for {name}")
-    if key in _compiled:
-        return _compiled[key]
-    path = os.path.join(_CACHE_DIR, f"{key}-{_source_tag()}.pkz")
+    variant = "-di" if os.environ.get("NZCB_WITNESS_DROP_IMPLIED") == "1" else ""  # builder.Circuit.assert_zero
+    ckey = key + variant
+    if ckey in _compiled:
+        return _compiled[ckey]
+    path = os.path.join(_CACHE_DIR, f"{key}-{_source_tag()}{variant}.pkz")
     if use_cache and os.path.exists(path):
         try:
             with open(path, "rb") as fh:
-                _compiled[key] = pickle.loads(zlib.decompress(fh.read()))
-            return _compiled[key]
+                _compiled[ckey] = pickle.loads(zlib.decompress(fh.read()))
+            return _compiled[ckey]
         except Exception:
             pass
     c = Circuit(key)
     MAINS[key](c)
     art = c.finalize().artifact()
-    _compiled[key] = art
+    _compiled[ckey] = art
     if use_cache and art.n_witness > 20000:
         os.makedirs(_CACHE_DIR, exist_ok=True)
         tmp = path + f".tmp{os.getpid()}"
         with open(tmp, "wb") as fh:
             fh.write(zlib.compress(pickle.dumps(art, protocol=4), 1))
         os.replace(tmp, path)
-    return _compiled[key]
+    return _compiled[ckey]
 
 
 class WasmTester:
