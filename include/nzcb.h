@@ -176,6 +176,16 @@ int32_t nzcb_circuit_info(const nzcb_circuit* c, uint32_t* n_witness, uint32_t* 
 int32_t nzcb_witness_batch(nzcb_ctx* ctx, const nzcb_circuit* c, const uint8_t* inputs_le, size_t B,
                            uint8_t* wtns_out, int32_t* status);
 
+/* The same for batches too large to bring every wire back (BASELINE.json configs[3]: 65,536 passes x 26 MB):
+ * outputs_le (may be NULL) receives w[1 .. nOutputs] of every pass (B x nOutputs x 32 B LE), i.e. what
+ * circom_tester's getDecoratedOutput / test/nzcp.js:62-68 reads; digest (may be NULL) receives one u64 per pass,
+ * sum_{i < nWitness, k < 8} (limb_k(w_i) + 1) * splitmix64(8 i + k) mod 2^64 over ALL wires of the pass, computed
+ * on the device; every pass i with i % sample_stride == 0 has its whole witness copied to wtns_sample_out
+ * (ceil(B / sample_stride) x nWitness x 32 B; NULL: none). */
+int32_t nzcb_witness_batch_ex(nzcb_ctx* ctx, const nzcb_circuit* c, const uint8_t* inputs_le, size_t B,
+                              uint8_t* outputs_le, uint64_t* digest, size_t sample_stride, uint8_t* wtns_sample_out,
+                              int32_t* status);
+
 /* snarkjs plonk.fullProve for B passes: witness program then prover, wires never leave HBM.
  * status[i] = 0, NZCB_E_ASSERT (pass rejected by the circuit) or a prover error; a failed
  * pass zeroes out[i] and never fails the batch. */

@@ -146,6 +146,12 @@ static napi_value FullProveBatch(napi_env env, napi_callback_info info) {
     NAPI_OK(napi_get_value_uint32(env, argv[3], &B));
     if (argc > 4 && !is_nullish(env, argv[4])) NAPI_OK(napi_get_buffer_info(env, argv[4], (void**)&bl, &blen));
     NZCB_OK_OR_THROW(nzcb_zkey_info(zk, NULL, &n_pub, NULL, NULL, NULL));
+    {   /* the library reads B * nInputs * 32 and B * 9 * 32 bytes: a short Buffer must not become an out-of-bounds read */
+        uint32_t n_in = 0;
+        NZCB_OK_OR_THROW(nzcb_circuit_info(c, NULL, &n_in, NULL));
+        if (ilen != (size_t)B * n_in * 32) { napi_throw_error(env, NULL, "nzcb: inputs must hold B * nInputs 32-byte values"); return NULL; }
+        if (bl && blen != (size_t)B * 9 * 32) { napi_throw_error(env, NULL, "nzcb: blinders must hold B * 9 32-byte values"); return NULL; }
+    }
     {
         nzcb_proof* proofs = (nzcb_proof*)malloc((size_t)(B ? B : 1) * sizeof(nzcb_proof));
         uint8_t* pub = (uint8_t*)malloc((size_t)(B ? B : 1) * (n_pub ? n_pub : 1) * 32);
@@ -174,6 +180,13 @@ static napi_value FullProveURIs(napi_env env, napi_callback_info info) {
     NAPI_OK(napi_get_value_uint32(env, argv[5], &max_len));
     if (olen < 4 || olen % 4) { napi_throw_error(env, NULL, "nzcb: uriOffsets must hold B + 1 u32 values"); return NULL; }
     B = (uint32_t)(olen / 4 - 1);
+    {   /* offsets ascending and inside the URI buffer; one 20-byte data value per pass */
+        uint32_t i;
+        for (i = 0; i < B; i++)
+            if (off[i] > off[i + 1]) { napi_throw_error(env, NULL, "nzcb: uriOffsets must be ascending"); return NULL; }
+        if (off[B] > ulen) { napi_throw_error(env, NULL, "nzcb: uriOffsets run past the end of uris"); return NULL; }
+        if (data && dlen != (size_t)B * 20) { napi_throw_error(env, NULL, "nzcb: data must hold B * 20 bytes"); return NULL; }
+    }
     NZCB_OK_OR_THROW(nzcb_zkey_info(zk, NULL, &n_pub, NULL, NULL, NULL));
     {
         nzcb_proof* proofs = (nzcb_proof*)malloc((size_t)(B ? B : 1) * sizeof(nzcb_proof));

@@ -73,6 +73,7 @@ SIGNATURES = {
     "nzcb_circuit_free": (None, [_vp]),
     "nzcb_circuit_info": (_i32, [_vp] + [ctypes.POINTER(_u32)] * 3),
     "nzcb_witness_batch": (_i32, [_vp, _vp, _vp, _sz, _vp, _vp]),
+    "nzcb_witness_batch_ex": (_i32, [_vp, _vp, _vp, _sz, _vp, _vp, _sz, _vp, _vp]),
     "nzcb_plonk_fullprove_batch": (_i32, [_vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp]),
     "nzcb_plonk_fullprove_batch_dev": (_i32, [_vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp]),
     "nzcb_vkey_from_zkey": (_i32, [_vp, _vp, _sz, ctypes.POINTER(_vp)]),

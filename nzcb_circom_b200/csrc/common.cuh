@@ -129,8 +129,9 @@ struct G1Table {
 int g1_table_build(nzcb_ctx* ctx, const G1Affine* d_bases, size_t n, G1Table* out, uint32_t window = 0);
 void g1_table_free(G1Table* t);
 // K <= 4 MSMs over the first n[k] bases of one table as a single batch; results in d_out[0..K)
+// sparse: most scalars are tiny (round 1 in the Lagrange basis): skip the batched-affine halving rounds
 int msm_table_dev(nzcb_ctx* ctx, const G1Table& tab, const uint32_t* const* d_scalars, const size_t* n, int K,
-                  bool scalars_mont, G1XYZZ* d_out);
+                  bool scalars_mont, G1XYZZ* d_out, bool sparse = false);
 // g1fft.cu : [L_i(tau)]G1 (i < 2^log_n) from [tau^j]G1 (j < 2^log_n); device buffers, in != out
 int g1_lagrange_basis(nzcb_ctx* ctx, const G1Affine* d_srs, uint32_t log_n, G1Affine* d_out);
 // D2H + stream sync + affine conversion of `count` <= 4 results

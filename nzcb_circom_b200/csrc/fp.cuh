@@ -368,4 +368,13 @@ struct alignas(32) Fp {
 typedef Fp<FrParams> Fr;
 typedef Fp<FqParams> Fq;
 
+// any 256-bit value -> [0, r): 2^256 < 6 r, five conditional subtractions.  The reduction has to come BEFORE a
+// Montgomery conversion or any multiply: the device's carry-chain multiply drops carries its operands cannot produce
+// when both are below the modulus, so an unreduced operand gives a wrong product there (the portable host multiply
+// is more forgiving, which is why a host check alone does not catch it).
+NZ_HD Fr fr_reduce_256(Fr x) {
+    for (int i = 0; i < 5; i++) x = Fr::reduce_once(x);
+    return x;
+}
+
 }  // namespace nzcb

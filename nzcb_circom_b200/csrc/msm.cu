@@ -32,6 +32,7 @@
 // Latency mode: a ctx may own only a slice of the point range (msm_table_finish exchanges the
 // partial sums).   Algorithmic work: n * 16 * 10 modmul in step 4.
 #include "common.cuh"
+#include "msm_affine.cuh"
 #include <stdlib.h>
 #include <algorithm>
 #include <vector>
@@ -47,6 +48,7 @@ struct MsmPlan {
     uint32_t G;      // bucket sets: K (table mode) or K * W (window mode)
     bool unified;    // table mode
     uint32_t stride; // table row stride (points)
+    bool sparse;     // caller's hint: most scalars are tiny (round 1 in the Lagrange basis) -- XYZZ walk only
 };
 
 static uint32_t floor_log2(size_t n) {
@@ -80,6 +82,7 @@ static MsmPlan make_plan_window(size_t n, int K) {
     p.G = (uint32_t)K * p.W;
     p.unified = false;
     p.stride = 0;
+    p.sparse = false;
     return p;
 }
 
@@ -249,30 +252,35 @@ static int scan_excl(nzcb_ctx* ctx, const uint32_t* counts, uint32_t* offsets, s
 // every other bucket it meets lies wholly inside the chunk and is written straight to buckets[].
 constexpr uint32_t ACC_THREADS = 256, ACC_LMIN = 8, ACC_LMAX = 64;
 
-// bucket holding the first entry of every chunk (binary search in the offsets, off the hot kernel's critical path)
+// bucket holding the first entry of every chunk (binary search in the offsets, off the hot kernel's critical path).
+// `shift`: the list has been through that many halving rounds (msm_affine.cuh), every offset is a multiple of 2^shift.
 __global__ void __launch_bounds__(256) k_msm_chunk_buckets(const uint32_t* __restrict__ offsets, uint32_t n_keys, uint32_t L,
-                                                           uint32_t* __restrict__ chunk_bucket, uint32_t max_chunks) {
+                                                           uint32_t shift, uint32_t* __restrict__ chunk_bucket,
+                                                           uint32_t max_chunks) {
     const uint32_t ch = blockIdx.x * blockDim.x + threadIdx.x;
     if (ch >= max_chunks) return;
-    const uint32_t E = offsets[n_keys];
+    const uint32_t E = offsets[n_keys] >> shift;
     const uint64_t lo = (uint64_t)ch * L;
     if (lo >= E) return;
     // the largest b with offsets[b] <= lo  (offsets[n_keys] = E > lo)
     uint32_t b = 0, z = n_keys;
     while (z - b > 1) {
         const uint32_t m = (b + z) >> 1;
-        if (offsets[m] <= (uint32_t)lo) b = m;
+        if ((offsets[m] >> shift) <= (uint32_t)lo) b = m;
         else z = m;
     }
     chunk_bucket[ch] = b;
 }
 
+// DIRECT: the list holds the points themselves (the output of the halving rounds), not references into `bases`.
+template <bool DIRECT>
 __global__ void __launch_bounds__(ACC_THREADS, 2)
     k_msm_accum(const G1Affine* __restrict__ bases, const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ offsets,
-                uint32_t n_keys, uint32_t L, const uint32_t* __restrict__ chunk_bucket, uint32_t* __restrict__ tile_counter,
-                G1XYZZ* __restrict__ buckets, uint32_t* __restrict__ pkeys, G1XYZZ* __restrict__ pvals) {
+                uint32_t n_keys, uint32_t L, uint32_t shift, const uint32_t* __restrict__ chunk_bucket,
+                uint32_t* __restrict__ tile_counter, G1XYZZ* __restrict__ buckets, uint32_t* __restrict__ pkeys,
+                G1XYZZ* __restrict__ pvals) {
     __shared__ uint32_t s_tile;
-    const uint32_t E = offsets[n_keys];
+    const uint32_t E = offsets[n_keys] >> shift;
     const uint32_t n_chunks = (uint32_t)(((uint64_t)E + L - 1) / L);
     const uint32_t n_tiles = (n_chunks + ACC_THREADS - 1) / ACC_THREADS;
     for (;;) {
@@ -286,18 +294,22 @@ __global__ void __launch_bounds__(ACC_THREADS, 2)
         const uint32_t lo = t * L;  // < E <= 2^32 - 1
         const uint32_t hi = (uint64_t)lo + L < E ? lo + L : E;
         uint32_t b = chunk_bucket[t];
-        uint32_t next = offsets[b + 1];
+        uint32_t next = offsets[b + 1] >> shift;
         G1XYZZ acc = G1XYZZ::inf();
         bool first = true;
-        uint32_t e = sorted[lo];
-        G1Affine p = bases[e & 0x7fffffffu];
+        uint32_t e = DIRECT ? 0u : sorted[lo];
+        G1Affine p = DIRECT ? bases[lo] : bases[e & 0x7fffffffu];
         for (uint32_t k = lo; k < hi; k++) {
             // prefetch the next point while this one is added
             const uint32_t e_cur = e;
             const G1Affine p_cur = p;
             if (k + 1 < hi) {
-                e = sorted[k + 1];
-                p = bases[e & 0x7fffffffu];
+                if (DIRECT) {
+                    p = bases[k + 1];
+                } else {
+                    e = sorted[k + 1];
+                    p = bases[e & 0x7fffffffu];
+                }
             }
             if (k == next) {  // bucket boundary: flush
                 if (first) {
@@ -310,11 +322,11 @@ __global__ void __launch_bounds__(ACC_THREADS, 2)
                 acc = G1XYZZ::inf();
                 do {
                     b++;
-                    next = offsets[b + 1];
+                    next = offsets[b + 1] >> shift;
                 } while (next == k);
             }
             G1Affine q = p_cur;
-            if (e_cur & 0x80000000u) q.y = q.y.neg();  // (0,0) stays (0,0)
+            if (!DIRECT && (e_cur & 0x80000000u)) q.y = q.y.neg();  // (0,0) stays (0,0)
             acc.add_affine(q);
         }
         if (first) {
@@ -326,6 +338,54 @@ __global__ void __launch_bounds__(ACC_THREADS, 2)
             pkeys[2 * t + 1] = b;
             pvals[2 * t + 1] = acc;
         }
+    }
+}
+
+// ---- step 4a: halving rounds with batched affine additions (msm_affine.cuh) ---------------------
+// counts -> multiples of 2^R, so that every bucket's segment of the sorted list is aligned for R rounds
+__global__ void __launch_bounds__(256) k_pad_counts(uint32_t* __restrict__ counts, size_t n, uint32_t R) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t m = (1u << R) - 1;
+    counts[i] = (counts[i] + m) & ~m;
+}
+// round `shift` (1-based): the input list has (*e_total >> (shift - 1)) entries, the output half as many
+template <bool REFS>
+__global__ void __launch_bounds__(256) k_aff_forward(const G1Affine* __restrict__ pts, const uint32_t* __restrict__ refs,
+                                                     const uint32_t* __restrict__ e_total, uint32_t shift,
+                                                     Fq* __restrict__ P, Fq* __restrict__ totals) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t n_add = *e_total >> shift;
+    if (REFS) {
+        const AffRefSrc src{pts, refs};
+        aff_forward_body(t, src, n_add, P, totals);
+    } else {
+        const AffPtSrc src{pts};
+        aff_forward_body(t, src, n_add, P, totals);
+    }
+}
+__global__ void __launch_bounds__(128) k_aff_invert(Fq* __restrict__ totals, Fq* __restrict__ tmp,
+                                                    const uint32_t* __restrict__ e_total, uint32_t shift) {
+    const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t n_add = *e_total >> shift;
+    const size_t n_tot = (n_add + AFF_M - 1) / AFF_M;
+    const size_t lo = s * AFF_INV_CHUNK;
+    if (lo >= n_tot) return;
+    aff_invert_chunk(totals, tmp, lo, lo + AFF_INV_CHUNK < n_tot ? lo + AFF_INV_CHUNK : n_tot);
+}
+template <bool REFS>
+__global__ void __launch_bounds__(256, 3) k_aff_backward(const G1Affine* __restrict__ pts, const uint32_t* __restrict__ refs,
+                                                         const uint32_t* __restrict__ e_total, uint32_t shift,
+                                                         const Fq* __restrict__ P, const Fq* __restrict__ totals_inv,
+                                                         G1Affine* __restrict__ out) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t n_add = *e_total >> shift;
+    if (REFS) {
+        const AffRefSrc src{pts, refs};
+        aff_backward_body(t, src, n_add, P, totals_inv, out);
+    } else {
+        const AffPtSrc src{pts};
+        aff_backward_body(t, src, n_add, P, totals_inv, out);
     }
 }
 
@@ -493,29 +553,40 @@ static int msm_run(nzcb_ctx* ctx, const G1Affine* d_bases, const MsmPlan& p, con
         NZ_LAUNCH(ctx, k_set_inf, 1, 32, 0, d_out, (uint32_t)K);
         return 0;
     }
-    if (n_sum * p.W >= ((size_t)1 << 32) || n_keys >= ((size_t)1 << 31))
-        return ctx->fail(NZCB_E_INVALID, "msm: batch too large");
+    if (n_keys >= ((size_t)1 << 31)) return ctx->fail(NZCB_E_INVALID, "msm: batch too large");
+
+    // halving rounds with batched affine additions first (msm_affine.cuh) when the buckets are full enough for the
+    // padding of their segments to multiples of 2^R to be cheap; the XYZZ walk finishes (or does everything, R = 0)
+    const size_t e_raw_max = n_sum * p.W;
+    uint32_t R = (!p.sparse && e_raw_max >= 24 * n_keys) ? 3 : 0;
+    {
+        const char* env = getenv("NZCB_MSM_AFFINE");
+        if (env && env[0] >= '0' && env[0] <= '5' && !env[1]) R = (uint32_t)(env[0] - '0');
+    }
+    const size_t e_max = e_raw_max + (((size_t)1 << R) - 1) * n_keys;  // upper bound of the padded list length
+    if (e_max >= ((size_t)1 << 32)) return ctx->fail(NZCB_E_INVALID, "msm: batch too large");
+    const size_t e_tail_max = (e_max >> R) + 1;                        // what the XYZZ walk sees
 
     // accumulation grid: persistent, one CTA per resident slot; chunk length from the entry-count upper bound
     static const int blocks_per_sm = [] {
-        int v = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_msm_accum, ACC_THREADS, 0) != cudaSuccess || v < 1) v = 1;
-        return v;
+        int v = 0, w = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_msm_accum<false>, ACC_THREADS, 0) != cudaSuccess || v < 1) v = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w, k_msm_accum<true>, ACC_THREADS, 0) != cudaSuccess || w < 1) w = 1;
+        return std::min(v, w);
     }();
-    const size_t e_max = n_sum * p.W;
     const uint32_t acc_slots = (uint32_t)ctx->sm_count * (uint32_t)blocks_per_sm;
-    uint32_t L = (uint32_t)std::min<size_t>(ACC_LMAX, std::max<size_t>(ACC_LMIN, e_max / ((size_t)acc_slots * ACC_THREADS * 4)));
+    uint32_t L = (uint32_t)std::min<size_t>(ACC_LMAX, std::max<size_t>(ACC_LMIN, e_tail_max / ((size_t)acc_slots * ACC_THREADS * 4)));
     {
         const char* env = getenv("NZCB_MSM_CHUNK");
         if (env && atoi(env) >= 1 && atoi(env) <= 4096) L = (uint32_t)atoi(env);
     }
-    const uint32_t max_chunks = (uint32_t)((e_max + L - 1) / L);
+    const uint32_t max_chunks = (uint32_t)((e_tail_max + L - 1) / L);
     const uint32_t acc_blocks = std::max<uint32_t>(1, std::min<uint32_t>(acc_slots, div_up(max_chunks, ACC_THREADS)));
     const uint32_t T1 = max_chunks;  // (key, partial) list: two slots per chunk
 
     uint32_t* counts = (uint32_t*)ctx->scratch_get("msm_counts", (n_keys + 1) * 4);
     uint32_t* offsets = (uint32_t*)ctx->scratch_get("msm_offsets", (n_keys + 1) * 4);
-    uint32_t* sorted = (uint32_t*)ctx->scratch_get("msm_sorted", n_sum * p.W * 4);
+    uint32_t* sorted = (uint32_t*)ctx->scratch_get("msm_sorted", e_max * 4);
     G1XYZZ* buckets = (G1XYZZ*)ctx->scratch_get("msm_buckets", n_keys * sizeof(G1XYZZ));
     uint32_t* pk0 = (uint32_t*)ctx->scratch_get("msm_pk0", (size_t)2 * T1 * 4);
     uint32_t* pk1 = (uint32_t*)ctx->scratch_get("msm_pk1", (size_t)2 * T1 * 4);
@@ -532,18 +603,35 @@ static int msm_run(nzcb_ctx* ctx, const G1Affine* d_bases, const MsmPlan& p, con
     if (!counts || !offsets || !sorted || !buckets || !pk0 || !pk1 || !pv0 || !pv1 || !rx0 || !rp0 || !rx1 || !rp1 ||
         !chunk_bucket || !tile_counter)
         return ctx->fail(NZCB_E_NOMEM, "msm: cannot allocate workspace for %zu scalars", n_sum);
+    // halving rounds: prefix products, batch totals, two point lists (round r reads one, writes the other)
+    Fq *aff_P = nullptr, *aff_tot = nullptr, *aff_tmp = nullptr;
+    G1Affine* aff_pts[2] = {nullptr, nullptr};
+    if (R) {
+        const size_t a1 = e_max / 2 + 1, t1 = a1 / AFF_M + 2;
+        aff_P = (Fq*)ctx->scratch_get("msm_aff_P", a1 * sizeof(Fq));
+        aff_tot = (Fq*)ctx->scratch_get("msm_aff_tot", t1 * sizeof(Fq));
+        aff_tmp = (Fq*)ctx->scratch_get("msm_aff_tmp", t1 * sizeof(Fq));
+        aff_pts[0] = (G1Affine*)ctx->scratch_get("msm_aff_pts0", a1 * sizeof(G1Affine));
+        aff_pts[1] = (G1Affine*)ctx->scratch_get("msm_aff_pts1", (a1 / 2 + 1) * sizeof(G1Affine));
+        if (!aff_P || !aff_tot || !aff_tmp || !aff_pts[0] || !aff_pts[1])
+            return ctx->fail(NZCB_E_NOMEM, "msm: cannot allocate the affine-round workspace for %zu scalars", n_sum);
+    }
 
     // 1-3: sort the point references by bucket
     NZ_CUDA(ctx, cudaMemsetAsync(counts, 0, (n_keys + 1) * 4, ctx->stream));
     const dim3 dgrid(div_up(n_max, 256), (unsigned)K);
     NZ_LAUNCH(ctx, k_msm_digits<true>, dgrid, 256, 0, da, counts, nullptr, nullptr);
+    if (R) {
+        NZ_LAUNCH(ctx, k_pad_counts, div_up(n_keys, 256), 256, 0, counts, n_keys, R);
+        NZ_CUDA(ctx, cudaMemsetAsync(sorted, 0xff, e_max * 4, ctx->stream));  // AFF_NULL in the padding slots
+    }
     NZ_TRY(scan_excl(ctx, counts, offsets, n_keys));
     NZ_CUDA(ctx, cudaMemsetAsync(counts, 0, (n_keys + 1) * 4, ctx->stream));
     NZ_LAUNCH(ctx, k_msm_digits<false>, dgrid, 256, 0, da, counts, offsets, sorted);
     NZ_CUDA(ctx, cudaMemsetAsync(buckets, 0, n_keys * sizeof(G1XYZZ), ctx->stream));  // ZZ = 0: infinity
     NZ_CUDA(ctx, cudaMemsetAsync(pk0, 0xff, (size_t)2 * T1 * 4, ctx->stream));            // KEY_NONE beyond the last chunk
     NZ_CUDA(ctx, cudaMemsetAsync(tile_counter, 0, 4, ctx->stream));
-    NZ_LAUNCH(ctx, k_msm_chunk_buckets, div_up(max_chunks, 256), 256, 0, offsets, (uint32_t)n_keys, L, chunk_bucket, max_chunks);
+    NZ_LAUNCH(ctx, k_msm_chunk_buckets, div_up(max_chunks, 256), 256, 0, offsets, (uint32_t)n_keys, L, R, chunk_bucket, max_chunks);
 
     // 4: accumulate
     if (ctx->prof_on) {
@@ -558,8 +646,30 @@ static int msm_run(nzcb_ctx* ctx, const G1Affine* d_bases, const MsmPlan& p, con
             NZ_CUDA(ctx, cudaMemcpyAsync(&ctx->prof_entries[ctx->prof_used], offsets + n_keys, 4, cudaMemcpyDeviceToHost, ctx->stream));
         NZ_CUDA(ctx, cudaEventRecord(ctx->prof_ev[ctx->prof_used].first, ctx->stream));
     }
-    NZ_LAUNCH(ctx, k_msm_accum, acc_blocks, ACC_THREADS, 0, d_bases, sorted, offsets, (uint32_t)n_keys, L, chunk_bucket,
-              tile_counter, buckets, pk0, pv0);
+    const uint32_t* e_total = offsets + n_keys;
+    for (uint32_t r = 1; r <= R; r++) {
+        const size_t adds = (e_max >> r) + 1;           // upper bound; the kernels read the count from e_total
+        const unsigned fb = div_up(div_up(adds, AFF_M), 256);
+        const unsigned ib = div_up(div_up(div_up(adds, AFF_M), AFF_INV_CHUNK), 128);
+        G1Affine* out = aff_pts[(r - 1) & 1];
+        if (r == 1) {
+            NZ_LAUNCH(ctx, k_aff_forward<true>, fb, 256, 0, d_bases, sorted, e_total, r, aff_P, aff_tot);
+            NZ_LAUNCH(ctx, k_aff_invert, ib, 128, 0, aff_tot, aff_tmp, e_total, r);
+            NZ_LAUNCH(ctx, k_aff_backward<true>, fb, 256, 0, d_bases, sorted, e_total, r, aff_P, aff_tot, out);
+        } else {
+            const G1Affine* in = aff_pts[r & 1];
+            NZ_LAUNCH(ctx, k_aff_forward<false>, fb, 256, 0, in, nullptr, e_total, r, aff_P, aff_tot);
+            NZ_LAUNCH(ctx, k_aff_invert, ib, 128, 0, aff_tot, aff_tmp, e_total, r);
+            NZ_LAUNCH(ctx, k_aff_backward<false>, fb, 256, 0, in, nullptr, e_total, r, aff_P, aff_tot, out);
+        }
+    }
+    if (R) {
+        NZ_LAUNCH(ctx, k_msm_accum<true>, acc_blocks, ACC_THREADS, 0, aff_pts[(R - 1) & 1], nullptr, offsets, (uint32_t)n_keys, L, R,
+                  chunk_bucket, tile_counter, buckets, pk0, pv0);
+    } else {
+        NZ_LAUNCH(ctx, k_msm_accum<false>, acc_blocks, ACC_THREADS, 0, d_bases, sorted, offsets, (uint32_t)n_keys, L, 0u,
+                  chunk_bucket, tile_counter, buckets, pk0, pv0);
+    }
     if (ctx->prof_on) {
         NZ_CUDA(ctx, cudaEventRecord(ctx->prof_ev[ctx->prof_used].second, ctx->stream));
         ctx->prof_used++;
@@ -650,7 +760,7 @@ void g1_table_free(G1Table* t) {
 }
 
 int msm_table_dev(nzcb_ctx* ctx, const G1Table& tab, const uint32_t* const* d_scalars, const size_t* n, int K,
-                  bool scalars_mont, G1XYZZ* d_out) {
+                  bool scalars_mont, G1XYZZ* d_out, bool sparse) {
     if (K < 1 || K > NZ_MSM_MAXJOBS) return ctx->fail(NZCB_E_INVALID, "msm: 1..%d jobs per batch", NZ_MSM_MAXJOBS);
     MsmJob jobs[NZ_MSM_MAXJOBS];
     for (int k = 0; k < K; k++) {
@@ -664,7 +774,7 @@ int msm_table_dev(nzcb_ctx* ctx, const G1Table& tab, const uint32_t* const* d_sc
         jobs[k] = MsmJob{d_scalars[k], lo, hi, scalars_mont};
     }
     MsmPlan p;
-    p.c = tab.c; p.W = tab.W; p.nbw = 1u << (tab.c - 1); p.G = (uint32_t)K; p.unified = true; p.stride = (uint32_t)tab.stride;
+    p.c = tab.c; p.W = tab.W; p.nbw = 1u << (tab.c - 1); p.G = (uint32_t)K; p.unified = true; p.stride = (uint32_t)tab.stride; p.sparse = sparse;
     return msm_run(ctx, tab.pts, p, jobs, K, d_out);
 }
 

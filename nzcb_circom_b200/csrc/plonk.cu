@@ -62,7 +62,7 @@ int parse_binfile(nzcb_ctx* ctx, const uint8_t* data, size_t len, const char* ma
         memcpy(&id, data + pos, 4);
         memcpy(&size, data + pos + 4, 8);
         pos += 12;
-        if (pos + size > len) return ctx->fail(NZCB_E_INVALID, "%s file: section %u overruns the file", magic, id);
+        if (size > len - pos) return ctx->fail(NZCB_E_INVALID, "%s file: section %u overruns the file", magic, id);
         if (!out.count(id)) out[id] = Section{data + pos, size};
         pos += size;
     }
@@ -115,7 +115,7 @@ __global__ void k_wtns_to_mont(const Fr* __restrict__ w_le, Fr* __restrict__ W, 
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_w) return;
     // "First element in plonk is not used ... We set it to zero" (A.2 step 0)
-    W[i] = i == 0 ? Fr::zero() : w_le[i].to_mont();
+    W[i] = i == 0 ? Fr::zero() : fr_reduce_256(w_le[i]).to_mont();  // a value >= r in a .wtns is taken mod r
 }
 
 __global__ void k_additions(const uint32_t* __restrict__ ia, const uint32_t* __restrict__ ib,
@@ -742,7 +742,7 @@ int prove_core(nzcb_ctx* ctx, const nzcb_zkey* zk, const Fr* d_w_le, const uint8
         {
             SideStream side(ctx, true);
             if (!side.ok) return ctx->fail(NZCB_E_CUDA, "prove: cannot set up the side stream");
-            NZ_TRY(msm_table_dev(ctx, zk->tab_lag, sc, sn, 3, true, b.pts));
+            NZ_TRY(msm_table_dev(ctx, zk->tab_lag, sc, sn, 3, true, b.pts, true));
         }
         const Fr pa[2] = {bl[2], bl[1]}, pb[2] = {bl[4], bl[3]}, pc[2] = {bl[6], bl[5]};
         NZ_TRY(to_coef(ctx, zk, b.A, b.pol_a, pa, 2));

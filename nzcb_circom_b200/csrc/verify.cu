@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(32) k_plonk_verify(const VkDev* __restrict__ v
             G1Affine pts[VERIFY_TERMS];
             Fr sc[VERIFY_TERMS];
             const bool ok = verify_prepare(*vkp, proofs + (size_t)b * sizeof(nzcb_proof), pubs + (size_t)b * n_pub * 32, n_pub,
-                                           pts, sc) && g2_on_curve(vkp->X2);
+                                           pts, sc) && !vkp->X2.is_inf() && g2_on_curve(vkp->X2);
             sm[w].ok = ok;
             if (ok)
                 for (int t = 0; t < VERIFY_TERMS; t++) {
@@ -220,6 +220,23 @@ int vkey_finish(nzcb_ctx* ctx, nzcb_vkey* vk, nzcb_vkey** out) {
     if (vk->h.power > 28) {
         delete vk;
         return ctx->fail(NZCB_E_INVALID, "verification key: power %u out of range", vk->h.power);
+    }
+    // X_2 = [tau]_2 must be a point of order r.  With X_2 at infinity e(., X_2) = 1 and the pairing check no longer
+    // binds the proof to the key (a forged proof with Z = Wxiw = infinity passes); a point of the twist outside the
+    // r-torsion would leave the pairing undefined.  Keys written without X_2 (all zero) can prove, not verify.
+    {
+        uint32_t r1[8];  // r - 1 (r is odd): [r - 1] X_2 == -X_2  <=>  [r] X_2 == infinity
+        for (int i = 0; i < 8; i++) r1[i] = Fr::modulus().v[i];
+        r1[0] -= 1;
+        bool ok = !vk->h.X2.is_inf() && g2_on_curve(vk->h.X2);
+        if (ok) {
+            const G2Affine m = g2_mul_limbs(vk->h.X2, r1);
+            ok = !m.is_inf() && m.x == vk->h.X2.x && m.y == vk->h.X2.y.neg();
+        }
+        if (!ok) {
+            delete vk;
+            return ctx->fail(NZCB_E_INVALID, "verification key: X_2 is not a point of order r (missing or invalid [tau]_2)");
+        }
     }
     // w = 5^((r-1)/2^28) squared down to the 2^power-th root
     Fr w = Fr::from_u64(5);

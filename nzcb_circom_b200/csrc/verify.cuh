@@ -42,14 +42,6 @@ NZ_HD void fr_to_be(const Fr& mont, uint8_t* be) {
         p[0] = (uint8_t)(c.v[i] >> 24), p[1] = (uint8_t)(c.v[i] >> 16), p[2] = (uint8_t)(c.v[i] >> 8), p[3] = (uint8_t)c.v[i];
     }
 }
-// any 256-bit value -> [0, r): 2^256 < 6 r, five conditional subtractions.  The reduction has to come BEFORE the
-// Montgomery conversion: the device's carry-chain multiply drops carries its operands cannot produce when both are
-// below the modulus (fp.cuh), so an unreduced digest gives a wrong product there (the portable host multiply is
-// more forgiving, which is why the host check alone did not catch it).
-NZ_HD Fr fr_reduce_256(Fr x) {
-    for (int i = 0; i < 5; i++) x = Fr::reduce_once(x);
-    return x;
-}
 // hashToFr: the 256-bit big-endian digest reduced mod r
 NZ_HD Fr hash_finish_fr(KeccakHD& k) {
     uint8_t d[32];

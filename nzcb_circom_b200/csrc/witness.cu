@@ -292,7 +292,8 @@ __global__ void __launch_bounds__(T, CTAS_PER_SM) k_witness(ProgView pv, const F
     for (uint32_t pass = blockIdx.x; pass < B; pass += gridDim.x) {
         Fr* W = wires + (size_t)pass * pv.n_total;
         const Fr* in = inputs + (size_t)pass * pv.n_in;
-        for (uint32_t i = threadIdx.x; i < pv.n_in; i += blockDim.x) W[1 + pv.n_out + i] = in[i];
+        // circom_runtime stores Fr.e(value): any 256-bit input is taken mod r (the multiply needs reduced operands)
+        for (uint32_t i = threadIdx.x; i < pv.n_in; i += blockDim.x) W[1 + pv.n_out + i] = fr_reduce_256(in[i]);
         if (threadIdx.x == 0) {
             Fr one = Fr::zero();
             one.v[0] = 1;
@@ -581,6 +582,79 @@ extern "C" int32_t nzcb_witness_batch(nzcb_ctx* ctx, const nzcb_circuit* c, cons
                                                ctx->stream));
             }
         }
+        NZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    NZ_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    NZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1);
+    return 0;
+}
+
+// ---- large batches: what 65,536 passes can afford to bring back (BASELINE.json configs[3]) ----------------------
+namespace {
+__device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+// digest[pass] = sum_{i < n_witness, k < 8} (w_i[k] + 1) * splitmix64(8 i + k)  mod 2^64 -- position dependent, order free
+__global__ void __launch_bounds__(256) k_witness_digest(const Fr* __restrict__ wires, uint32_t n_total, uint32_t n_witness,
+                                                        uint64_t* __restrict__ digest) {
+    __shared__ uint64_t part[8];
+    const Fr* W = wires + (size_t)blockIdx.x * n_total;
+    uint64_t acc = 0;
+    for (uint32_t i = threadIdx.x; i < n_witness; i += blockDim.x) {
+        const Fr w = W[i];
+#pragma unroll
+        for (uint32_t k = 0; k < 8; k++) acc += ((uint64_t)w.v[k] + 1) * splitmix64(8ull * i + k);
+    }
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint64_t t = 0;
+        for (int w = 0; w < 8; w++) t += part[w];
+        digest[blockIdx.x] = t;
+    }
+}
+}  // namespace
+
+extern "C" int32_t nzcb_witness_batch_ex(nzcb_ctx* ctx, const nzcb_circuit* c, const uint8_t* inputs_le, size_t B,
+                                         uint8_t* outputs_le, uint64_t* digest, size_t sample_stride,
+                                         uint8_t* wtns_sample_out, int32_t* status) {
+    if (!ctx || !c || (!inputs_le && c->n_in) || !status || (wtns_sample_out && sample_stride == 0)) return NZCB_E_INVALID;
+    if (c->ctx != ctx) return ctx->fail(NZCB_E_INVALID, "circuit was loaded on a different context");
+    if (B == 0) return 0;
+    NZ_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t per_pass = (size_t)c->n_total * sizeof(Fr);
+    size_t chunk = std::max<size_t>(1, ((size_t)8 << 30) / per_pass);
+    if (chunk > B) chunk = B;
+    Fr* d_w = (Fr*)ctx->scratch_get("wt_wires", chunk * per_pass);
+    Fr* d_in = (Fr*)ctx->scratch_get("wt_inputs", std::max<size_t>(32, chunk * (size_t)c->n_in * sizeof(Fr)));
+    int32_t* d_st = (int32_t*)ctx->scratch_get("wt_status", chunk * sizeof(int32_t));
+    uint64_t* d_dg = (uint64_t*)ctx->scratch_get("wt_digest", chunk * sizeof(uint64_t));
+    if (!d_w || !d_in || !d_st || !d_dg) return ctx->fail(NZCB_E_NOMEM, "witness: cannot allocate %zu device bytes", chunk * per_pass);
+    NZ_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    for (size_t done = 0; done < B; done += chunk) {
+        const size_t nb = std::min(chunk, B - done);
+        if (c->n_in)
+            NZ_CUDA(ctx, cudaMemcpyAsync(d_in, inputs_le + done * (size_t)c->n_in * 32, nb * (size_t)c->n_in * 32,
+                                         cudaMemcpyHostToDevice, ctx->stream));
+        NZ_TRY(witness_dev(ctx, c, d_in, nb, d_w, d_st));
+        NZ_CUDA(ctx, cudaMemcpyAsync(status + done, d_st, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        if (digest) {
+            NZ_LAUNCH(ctx, k_witness_digest, (unsigned)nb, 256, 0, d_w, c->n_total, c->n_witness, d_dg);
+            NZ_CUDA(ctx, cudaMemcpyAsync(digest + done, d_dg, nb * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        if (outputs_le && c->n_out)
+            NZ_CUDA(ctx, cudaMemcpy2DAsync(outputs_le + done * (size_t)c->n_out * 32, (size_t)c->n_out * 32, d_w + 1, per_pass,
+                                           (size_t)c->n_out * 32, nb, cudaMemcpyDeviceToHost, ctx->stream));
+        if (wtns_sample_out)
+            for (size_t i = (done + sample_stride - 1) / sample_stride * sample_stride; i < done + nb; i += sample_stride)
+                NZ_CUDA(ctx, cudaMemcpyAsync(wtns_sample_out + (i / sample_stride) * (size_t)c->n_witness * 32,
+                                             d_w + (i - done) * (size_t)c->n_total, (size_t)c->n_witness * 32,
+                                             cudaMemcpyDeviceToHost, ctx->stream));
         NZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
     NZ_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));

@@ -48,7 +48,11 @@ class CircuitProver:
         self.timings["srs"] = time.time() - t
         t = time.time()
         # X_2 = [tau]_2 when the trapdoor is known (the synthetic SRS); an external SRS must bring its own
-        x2 = powersoftau.new_g2(self.tau % _R, self.ctx) if self.tau is not None and x2_g2_lem is None else (x2_g2_lem or bytes(128))
+        if x2_g2_lem is None:
+            if self.tau is None:
+                raise ValueError("an external SRS must come with its X_2 = [tau]_2 (x2_g2_lem)")
+            x2_g2_lem = powersoftau.new_g2(self.tau % _R, self.ctx)
+        x2 = x2_g2_lem
         zkey = plonk.setup(r1cs, srs_g1_lem, x2, self.ctx)
         self.timings["setup"] = time.time() - t
         t = time.time()

@@ -206,7 +206,7 @@ class _Plonk:
             raw = b"".join(p if isinstance(p, (bytes, bytearray)) else proof_obj_to_bytes(p) for p in proofs)
             if len(raw) != 800 * B:
                 raise ValueError("a raw proof is 800 bytes")
-            pubs = b"".join((int(x) % (1 << 256)).to_bytes(32, "little") for ps in publics_list for x in ps)
+            pubs = b"".join((int(x) % R_MOD).to_bytes(32, "little") for ps in publics_list for x in ps)  # snarkjs: Fr.e(x)
             valid = (ctypes.c_int32 * B)()
             ctx.check(ctx.lib.nzcb_plonk_verify_batch(ctx.h, vkey.h, as_cbuf(raw), as_cbuf(pubs or b"\0"), n_pub, B, valid))
             return [bool(v) for v in valid]
@@ -222,7 +222,7 @@ class _Plonk:
         lib = load()
         raw = proof if isinstance(proof, (bytes, bytearray)) else proof_obj_to_bytes(proof)
         ps = Proof.from_buffer_copy(raw)
-        pubs = b"".join(int(x).to_bytes(32, "little") for x in publicSignals)
+        pubs = b"".join((int(x) % R_MOD).to_bytes(32, "little") for x in publicSignals)
         n = ctypes.c_size_t(0)
         lib.nzcb_proof_to_calldata(ctypes.byref(ps), as_cbuf(pubs or b"\0"), len(publicSignals), None, ctypes.byref(n))
         buf = ctypes.create_string_buffer(n.value)
@@ -243,10 +243,16 @@ class _Plonk:
             raise NzcbError(rc, "proof_to_json failed")
         return buf.value.decode()
 
-    def setup(self, r1cs, srs_g1_lem, x2_g2_lem=bytes(128), ctx=None):
+    def setup(self, r1cs, srs_g1_lem, x2_g2_lem, ctx=None):
         """`snarkjs plonk setup circuit.r1cs pot.ptau circuit.zkey` (the ptau reduced to its
-        tauG1 points, affine LEM, as section 2 of the .ptau holds them)."""
+        tauG1 points, affine LEM, as section 2 of the .ptau holds them, and X_2 = tauG2[1], 128 bytes LEM).
+        X_2 is required: a key written with X_2 = 0 makes every verifier that trusts it accept forged proofs
+        (plonk.verify here refuses such a key).  `allow_missing_x2` is the explicit way to write a prove-only key."""
         ctx = ctx or default_context()
+        if x2_g2_lem is None or len(x2_g2_lem) != 128:
+            raise ValueError("plonk setup: X_2 ([tau]_2, 128 bytes) is required")
+        if not any(x2_g2_lem) and not getattr(self, "allow_missing_x2", False):
+            raise ValueError("plonk setup: X_2 is all zero (the point at infinity); the key could not be verified against")
         r = _bytes_of(r1cs)
         rbuf, sbuf = as_cbuf(r), as_cbuf(bytes(srs_g1_lem))
         x2 = (ctypes.c_uint8 * 128).from_buffer_copy(x2_g2_lem)

@@ -100,3 +100,38 @@ extern "C" int fc_plonk_verify(const uint8_t* vkb, const uint8_t* proof, const u
     memcpy(vk.Q, vkb + 104, 512); memcpy(&vk.X2, vkb + 616, 128);
     return verify_serial(vk, proof, pubs, n_pub) ? 1 : 0;
 }
+
+// ---- batched affine bucket additions (csrc/msm_affine.cuh): the halving rounds' thread bodies, run serially ----
+#include "../../nzcb_circom_b200/csrc/msm_affine.cuh"
+#include <vector>
+// bases: n_bases x 64 B affine LEM.  refs: the padded, bucket-sorted list (n_refs a multiple of 2^R; AFF_NULL padding;
+// bit 31 = negate).  Runs R rounds exactly as msm.cu launches them and writes the (n_refs >> R) surviving points.
+extern "C" int fc_affine_rounds(const uint8_t* bases, uint32_t n_bases, const uint32_t* refs, uint32_t n_refs, uint32_t R,
+                                uint8_t* out) {
+    if (n_refs & ((1u << R) - 1)) return -1;
+    std::vector<G1Affine> B(n_bases ? n_bases : 1);
+    memcpy(B.data(), bases, (size_t)n_bases * 64);
+    std::vector<G1Affine> cur, nxt;
+    for (uint32_t r = 1; r <= R; r++) {
+        const size_t n_add = n_refs >> r;
+        const size_t n_thr = (n_add + AFF_M - 1) / AFF_M;
+        std::vector<Fq> P(n_add + 1), tot(n_thr + 1), tmp(n_thr + 1);
+        nxt.assign(n_add + 1, G1Affine::inf());
+        for (size_t t = 0; t < n_thr + 2; t++) {  // two threads beyond the end: they must do nothing
+            if (r == 1) aff_forward_body(t, AffRefSrc{B.data(), refs}, n_add, P.data(), tot.data());
+            else aff_forward_body(t, AffPtSrc{cur.data()}, n_add, P.data(), tot.data());
+        }
+        for (size_t s = 0; s * AFF_INV_CHUNK < n_thr; s++) {
+            const size_t lo = s * AFF_INV_CHUNK, hi = lo + AFF_INV_CHUNK < n_thr ? lo + AFF_INV_CHUNK : n_thr;
+            aff_invert_chunk(tot.data(), tmp.data(), lo, hi);
+        }
+        for (size_t t = 0; t < n_thr + 2; t++) {
+            if (r == 1) aff_backward_body(t, AffRefSrc{B.data(), refs}, n_add, P.data(), tot.data(), nxt.data());
+            else aff_backward_body(t, AffPtSrc{cur.data()}, n_add, P.data(), tot.data(), nxt.data());
+        }
+        cur.swap(nxt);
+    }
+    if (R == 0) return -1;
+    memcpy(out, cur.data(), (size_t)(n_refs >> R) * 64);
+    return 0;
+}

@@ -77,3 +77,50 @@ def test_keccak(fc):
         out = ctypes.create_string_buffer(32)
         fc.fc_keccak256(d, ctypes.c_size_t(n), out)
         assert out.raw == keccak256(d)
+
+
+def test_affine_rounds(fc):
+    """msm_affine.cuh: R halving rounds over a padded, bucket-sorted reference list leave, per bucket, points whose
+    sum is the bucket's sum -- with null padding, infinity bases, negated references, equal points (doubling) and
+    cancelling pairs inside the batches, and batch / chunk sizes that do not divide the list."""
+    rng = random.Random(11)
+    n_bases = 90
+    pts = []
+    P = b.g1_mul(b.G1_GEN, rng.randrange(1, b.R_MOD))
+    step = b.g1_mul(b.G1_GEN, rng.randrange(1, b.R_MOD))
+    for _ in range(n_bases):
+        pts.append(P)
+        P = b.g1_add(P, step)
+    pts[5] = None                     # infinity base
+    pts[7] = pts[6]                   # equal bases
+    pts[9] = b.g1_neg(pts[8])         # cancelling pair
+    bases = b"".join(b.g1_to_lem(p) for p in pts)
+    NULL = 0xFFFFFFFF
+    for R, n_buckets in ((1, 40), (3, 300), (3, 7), (2, 1100)):
+        refs, want = [], []
+        for bk in range(n_buckets):
+            cnt = rng.choice([0, 1, 2, 3, 5, 8, 9, 17, 40]) if n_buckets < 1000 else rng.choice([0, 1, 2, 7])
+            seg = []
+            for _ in range(cnt):
+                i = rng.randrange(n_bases)
+                if rng.random() < 0.3:
+                    i = rng.choice([5, 6, 7, 8, 9])  # provoke inf + P, P + P, P - P
+                seg.append(i | (rng.getrandbits(1) << 31))
+            if bk == 0 and R == 3:
+                seg = [6, 7, 6 | 1 << 31, 7 | 1 << 31, 8, 9, 5, 5, 8 | 1 << 31, 9 | 1 << 31][:cnt] + seg[10:]
+            acc = None
+            for e in seg:
+                p = pts[e & 0x7FFFFFFF]
+                acc = b.g1_add(acc, b.g1_neg(p) if (e >> 31) and p is not None else p)
+            pad = (-len(seg)) % (1 << R)
+            want.append((len(refs) >> R, (len(seg) + pad) >> R, acc))
+            refs += seg + [NULL] * pad
+        n_refs = len(refs)
+        arr = (ctypes.c_uint32 * max(1, n_refs))(*refs)
+        out = ctypes.create_string_buffer(max(64, (n_refs >> R) * 64))
+        assert fc.fc_affine_rounds(bases, n_bases, arr, n_refs, R, out) == 0
+        for lo, cnt, acc in want:
+            got = None
+            for k in range(lo, lo + cnt):
+                got = b.g1_add(got, b.g1_from_lem(out.raw[64 * k:64 * k + 64]))
+            assert got == acc

@@ -44,6 +44,13 @@ def test_find_cred_subj_example(backend):  # :155-166 (pos 77 -> 246)
     assert w[1] == 246
 
 
+def test_find_cred_subj_live(backend):  # :168-199 (findCredSubj_liveTest: pos 81 -> 250) on synthetic live-layout passes
+    for seed in (3, 8):
+        p = H.synth_pass(seed)
+        w = calc("findCredSubj_liveTest", {"mapLen": 4, "bytes": list(H.fitBytes(p["toBeSigned"], 351)), "pos": 81}, backend)
+        assert w[1] == 250
+
+
 def _check_cred_subj(w, buf, given, family, dob):  # testReadCredSubj :201-229
     assert w[1:1 + buf] == H.padArray(H.stringToArray(given), buf) and w[1 + buf] == len(given)
     assert w[2 + buf:2 + 2 * buf] == H.padArray(H.stringToArray(family), buf) and w[2 + 2 * buf] == len(family)

@@ -138,35 +138,138 @@ def test_nzcp_live_proof_bytes_equal_c_oracle_full_size(nzcp_live_prover):
     assert st == 0 and gproof == cproof and [int(x) for x in gpub] == list(cpub)
 
 
+def test_nzcp_example_setup_prove_verify(ctx):
+    """BASELINE.json configs[0]: the nzcp_example circuit (/root/reference/circuits/nzcp_example.circom:4,
+    Makefile:54-57 `plonk setup` / `zkey export verificationkey`) through powersoftau -> plonk setup -> fullProve ->
+    verify on the GPU, for the reference's own EXAMPLE_PASS_URI (test/nzcp.js:71): public signals are the golden
+    outputs the reference's test reads, the proof is byte-identical to the C oracle's, the device verifier and the
+    oracle's verifier accept it and reject a tampered copy."""
+    import json
+    import os
+
+    from nzcb_circom_b200.prover import NzcpProver, default_tau
+    from oracle import c_oracle as C
+
+    pr = NzcpProver(live=False, tau=default_tau(), ctx=ctx)
+    zkey = pr.setup(keep_zkey=True)
+    assert pr.zk.n_public == 3 and pr.zk.domain_size == 1 << pr.power
+    cose = H.getCOSE(H.EXAMPLE_PASS_URI)
+    tbs = H.encodeToBeSigned(cose["bodyProtected"], cose["payload"])
+    data = bytes(range(1, 21))
+    p2 = H.synth_pass(77, live=False)
+    items = [(tbs, data), (p2["toBeSigned"], p2["data"])]
+    bl = [list(range(21, 30)), list(range(31, 40))]
+    res = pr.prove_passes(items, bl)
+    assert [r[2] for r in res] == [0, 0]
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_vectors.json")) as fh:
+        golden = json.load(fh)
+    pub0 = [int(x) for x in res[0][1]]
+    assert pub0 == [int(x) for x in golden["public_outputs"]["value"]]
+    nh, th, exp, d = H.nzcp_decode_outputs(pub0)
+    assert th == hashlib.sha256(tbs).digest() and exp == 1951416330 and d == data
+    assert nh == hashlib.sha512(H.fitBytes(b"Jack,Sparrow,1960-04-16", 64)).digest()[:32]
+    C.use_all_cores()
+    inp = pr.marshal_passes(items[:1])
+    rc, cproof, cpub = C.fullprove(pr.art.wprog_bytes(), inp, zkey, bl[0], 3)
+    assert rc == 0 and cproof == res[0][0] and list(cpub) == pub0
+    vk = oplonk.vk_from_json(pr.vk)
+    for proof, public, _ in res:
+        pub = [int(x) for x in public]
+        assert oplonk.verify_with_trapdoor(vk, pub, oplonk.proof_from_bytes(proof), TAU)
+    bad = bytearray(res[1][0])
+    bad[640] ^= 1
+    pubs = [res[0][1], res[1][1], res[1][1]]
+    assert pr.verify(pubs, [res[0][0], res[1][0], bytes(bad)]) == [True, True, False]
+    pr.zk.close()
+
+
+def _wires_digest(raw, n_witness):
+    """the digest nzcb_witness_batch_ex computes on the device (include/nzcb.h), over host wires"""
+    import numpy as np
+
+    w = np.frombuffer(raw, dtype="<u4", count=n_witness * 8).astype(np.uint64)
+    z = np.arange(n_witness * 8, dtype=np.uint64) + np.uint64(0x9E3779B97F4A7C15)
+    z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    z ^= z >> np.uint64(31)
+    return int(((w + np.uint64(1)) * z).sum(dtype=np.uint64))
+
+
 def test_witness_batch_65536_passes(ctx):
     """BASELINE.json configs[3] at full size: 65,536 nzcp_live passes through the batched witness program (8 calls of
-    8,192 sharing one marshalled buffer).  Size-independent property: exactly the corrupted passes are rejected
-    ("Assert Failed"), every other pass is accepted -- a failed pass never fails its batch."""
+    8,192), 4,096 DISTINCT synthetic passes plus corrupted ones.  Checked for every pass: the status flag (exactly
+    the corrupted passes are rejected, a failed pass never fails its batch), the three public outputs against
+    hashlib / the pass itself, and a device-side digest over ALL of the pass's wires -- equal for every copy of a
+    pass wherever it sits in the batch, and equal to the digest of the C oracle's witness for a sample of the
+    distinct passes.  For a strided sample the whole witness comes back and is compared wire for wire."""
     import ctypes
 
     from nzcb_circom_b200.circom_tester import wasm_tester
+    from oracle import c_oracle as C
 
     cir = wasm_tester("nzcp_live", ctx)
     art = cir.compiled
+    n_out, n_wit = art.n_out, art.n_witness
+    D, B, CALLS, STRIDE = 4096, 8192, 8, 1021
+    passes = [H.synth_pass(500 + s) for s in range(D)]
     distinct = []
-    for s in range(32):
-        p = H.synth_pass(500 + s)
+    for p in passes:
         vals = art.flatten_input(H.nzcp_input(p["toBeSigned"], 351, p["data"]))
         distinct.append(b"".join(int(v).to_bytes(32, "little") for v in vals))
+    want_pub = []
+    for p in passes:
+        nh = hashlib.sha512(H.fitBytes(p["nullifier"].encode(), 64)).digest()[:32]
+        want_pub.append((nh, hashlib.sha256(p["toBeSigned"]).digest(), p["exp"], p["data"]))
     bad = bytearray(distinct[0])
     bad[0:32] = (2).to_bytes(32, "little")  # first ToBeSigned bit is not boolean (nzcptpl.circom:493-496)
-    B = 8192
-    rows = [distinct[i % 32] for i in range(B)]
-    bad_at = set(range(5, B, 1021))
-    for i in bad_at:
-        rows[i] = bytes(bad)
-    buf = b"".join(rows)
-    status = (ctypes.c_int32 * B)()
     h = cir._handle(ctx)
+    wprog = art.wprog_bytes()
+    oracle_digest = {}
+    pub_seen = {}
     total_ms = 0.0
-    for _ in range(8):
-        ctx.check(ctx.lib.nzcb_witness_batch(ctx.h, h, buf, B, None, status))
+    n_sample = (B + STRIDE - 1) // STRIDE
+    for call in range(CALLS):
+        # a different arrangement of the distinct passes in every call, so a pass meets many batch positions
+        idx = [(i * (2 * call + 1) + 37 * call) % D for i in range(B)]
+        bad_at = set(range(5 + call, B, 1021))
+        rows = [bytes(bad) if i in bad_at else distinct[idx[i]] for i in range(B)]
+        buf = b"".join(rows)
+        status = (ctypes.c_int32 * B)()
+        outputs = ctypes.create_string_buffer(B * n_out * 32)
+        digest = (ctypes.c_uint64 * B)()
+        sample = ctypes.create_string_buffer(n_sample * n_wit * 32)
+        ctx.check(ctx.lib.nzcb_witness_batch_ex(ctx.h, h, buf, B, outputs, digest, STRIDE, sample, status))
         total_ms += ctx.last_device_ms
         st = list(status)
         assert all((st[i] == -6) == (i in bad_at) and st[i] in (0, -6) for i in range(B))
-    print(f"65,536 passes in {total_ms:.0f} ms of device time ({65536 / total_ms * 1e3:.0f} passes/s)")
+        first_digest = {}
+        out_raw = outputs.raw
+        for i in range(B):
+            if i in bad_at:
+                continue
+            d = idx[i]
+            raw_pub = out_raw[i * n_out * 32:(i + 1) * n_out * 32]
+            if d not in pub_seen:    # decoded once per distinct pass; every other copy must carry the same bytes
+                pub = [int.from_bytes(raw_pub[k * 32:(k + 1) * 32], "little") for k in range(n_out)]
+                assert H.nzcp_decode_outputs(pub) == want_pub[d], (call, i)
+                pub_seen[d] = raw_pub
+            assert pub_seen[d] == raw_pub, (call, i)
+            assert first_digest.setdefault(d, digest[i]) == digest[i], (call, i)   # position independent
+        # anchor the digests and the sampled witnesses on the C oracle (a few passes per call: 2 s each on one core)
+        for k in range(n_sample):
+            i = k * STRIDE
+            if i in bad_at or k % 4 != call % 4:
+                continue
+            d = idx[i]
+            if d not in oracle_digest:
+                rc, wires = C.witness(wprog, distinct[d], art.n_total)
+                assert rc == 0
+                oracle_digest[d] = (_wires_digest(wires, n_wit), wires[:n_wit * 32])
+            assert digest[i] == oracle_digest[d][0], (call, i)
+            assert bytes(memoryview(sample)[k * n_wit * 32:(k + 1) * n_wit * 32]) == oracle_digest[d][1], (call, i)
+        for d, (dg, _) in oracle_digest.items():
+            if d in first_digest:
+                assert first_digest[d] == dg
+    assert len(oracle_digest) >= 8 and len(pub_seen) == D
+    print(f"65,536 passes in {total_ms:.0f} ms of device time ({65536 / total_ms * 1e3:.0f} passes/s), "
+          f"{len(oracle_digest)} witnesses compared wire for wire with the C oracle")

@@ -152,7 +152,7 @@ def test_table_msm_giant_buckets(ctx):
     tab.close()
 
 
-@pytest.mark.parametrize("log_n", [16, 21])
+@pytest.mark.parametrize("log_n", [16, 17, 18, 19, 20, 21, 22])
 def test_table_msm_srs_identity_large(ctx, log_n):
     """sum_i c_i [tau^i]G == p(tau) G for the synthetic SRS, full-size scalars and wire-like small ones;
     table mode and one-shot window mode agree bit for bit."""

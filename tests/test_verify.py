@@ -201,6 +201,49 @@ def test_gpu_verify_matches_the_oracle(ctx, name):
     vkey.close()
 
 
+def _twist_point_outside_g2(rng):
+    """a point of the sextic twist y^2 = x^3 + 3/(9+u) that is NOT of order r (the twist's cofactor is ~2^254)"""
+    q = b.P_MOD
+    one, mone = (1, 0), (q - 1, 0)
+    while True:
+        x = (rng.randrange(q), rng.randrange(q))
+        a = pg.f2_add(pg.f2_mul(pg.f2_sqr(x), x), pg.TWIST_B)
+        a1 = pg.f2_pow(a, (q - 3) // 4)                      # square root in Fq2, q = 3 mod 4
+        alpha = pg.f2_mul(pg.f2_sqr(a1), a)
+        if pg.f2_mul(pg.f2_conj(alpha), alpha) == mone:
+            continue                                         # not a square
+        x0 = pg.f2_mul(a1, a)
+        y = pg.f2_mul((0, 1), x0) if alpha == mone else pg.f2_mul(pg.f2_pow(pg.f2_add(one, alpha), (q - 1) // 2), x0)
+        Q = (x, y)
+        assert pg.g2_is_on_curve(Q)
+        if pg.g2_add(pg.g2_mul(Q, b.R_MOD - 1), Q) is not None:  # [r] Q != infinity
+            return Q
+
+
+@pytest.mark.gpu
+def test_gpu_vkey_refuses_a_key_without_a_valid_x2(ctx):
+    """with X_2 at infinity e(., X_2) = 1, the pairing check degenerates to B1 == infinity and a forged
+    proof (Z = Wxiw = infinity, eval_zw = 0, Wxi = -(F - E)/xi) passes.  Such a key -- and one whose X_2 lies on the
+    twist outside the r-torsion -- must not load as a verification key at all."""
+    from nzcb_circom_b200 import NzcbError
+    from nzcb_circom_b200.snarkjs import VKey, plonk, zKey
+
+    fx, zkey, vk, proof, pub = _fixture("small")
+    with pytest.raises(NzcbError):
+        VKey(zkey, ctx)                                      # the fixture zkey was written without X_2 (all zero)
+    vkj = zKey.exportVerificationKey(zkey)
+    vkj["X_2"] = [["0", "0"], ["0", "0"], ["0", "0"]]
+    with pytest.raises(NzcbError):
+        plonk.verify(vkj, pub, proof, ctx)
+    Q = _twist_point_outside_g2(random.Random(3))
+    vkj["X_2"] = [[str(Q[0][0]), str(Q[0][1])], [str(Q[1][0]), str(Q[1][1])], ["1", "0"]]
+    with pytest.raises(NzcbError):
+        plonk.verify(vkj, pub, proof, ctx)
+    vkj["X_2"] = [["1", "2"], ["3", "4"], ["1", "0"]]     # not on the twist
+    with pytest.raises(NzcbError):
+        plonk.verify(vkj, pub, proof, ctx)
+
+
 @pytest.mark.gpu
 def test_gpu_nzcp_live_proofs_verify_on_the_device(nzcp_live_prover):
     """full size: prove on the GPU, verify on the GPU with the key taken from the zkey itself (X_2 = [tau]_2 from

@@ -57,7 +57,7 @@ def main():
     ctx = Context(0)
     n = 1 << power
     t = time.time(); srs = powersoftau.new_g1(tau, n + 6, ctx); print(f"srs: {time.time()-t:.2f}s", flush=True)
-    t = time.time(); zkey = plonk.setup(r1cs, srs, bytes(128), ctx); print(f"setup: {time.time()-t:.2f}s zkey={len(zkey)/2**30:.2f} GiB", flush=True)
+    t = time.time(); zkey = plonk.setup(r1cs, srs, powersoftau.new_g2(tau, ctx), ctx); print(f"setup: {time.time()-t:.2f}s zkey={len(zkey)/2**30:.2f} GiB", flush=True)
     t = time.time(); zk = ZKey(zkey, ctx); print(f"zkey load: {time.time()-t:.2f}s n={zk.domain_size} nVars={zk.n_vars} nAdd={zk.n_additions}", flush=True)
     vk = oplonk.verification_key(zkey[:4096 + 2000])if False else None
     bl = list(range(101, 110))
