@@ -93,8 +93,72 @@ def make_passes(rank, step, batch):
     return [(p["toBeSigned"], p["data"]) for p in make_pass_dicts(rank, step, batch)]
 
 
+def _snarkjs_available():
+    """node on PATH and snarkjs resolvable (NZCB_NODE_MODULES = a node_modules directory holding the reference's
+    dependencies, e.g. a `yarn install`ed checkout of noway/nzcb-circom).  Never true in the build image."""
+    import shutil
+    node = shutil.which("node")
+    if not node:
+        return None
+    nm = os.environ.get("NZCB_NODE_MODULES")
+    probe = "require.resolve('snarkjs')" if not nm else f"require('module').createRequire({json.dumps(os.path.join(nm, '_'))}).resolve('snarkjs')"
+    try:
+        if subprocess.run([node, "-e", probe], capture_output=True, timeout=30).returncode != 0:
+            return None
+    except Exception:
+        return None
+    return node, nm
+
+
+def run_reference_snarkjs(args, node, nm, pr, zkey):
+    """The real reference path: snarkjs.plonk.prove on Node (baseline/snarkjs_baseline.mjs) over the zkey / wtns this
+    repository wrote, blinders injected, proof bytes compared.  Returns the JSON line or None."""
+    import tempfile
+
+    from nzcb_circom_b200 import nzcp_helpers as H
+    from nzcb_circom_b200.snarkjs import plonk, wtns_from_raw
+
+    steps = args.steps if args.steps is not None else 2
+    with tempfile.TemporaryDirectory() as d:
+        p = H.synth_pass(0)
+        raw, st = pr.tester.calculateWitnessBatch([H.nzcp_input(p["toBeSigned"], 351, p["data"])], True, pr.ctx)
+        wt = wtns_from_raw(raw)
+        bl = list(range(1, 10))
+        proof, public = plonk.prove(pr.zk, wt, blinders=bl, raw=True)
+        for name, data in (("circuit.zkey", bytes(zkey)), ("witness.wtns", bytes(wt))):
+            with open(os.path.join(d, name), "wb") as f:
+                f.write(data)
+        for name, text in (("blinders.json", json.dumps([str(x) for x in bl])), ("proof.json", plonk.proof_json(proof, pr.ctx)),
+                           ("public.json", json.dumps([str(int(x)) for x in public])),
+                           ("verification_key.json", json.dumps(pr.vk, indent=1))):
+            with open(os.path.join(d, name), "w") as f:
+                f.write(text)
+        cmd = [node, "--max-old-space-size=16384", os.path.join(ROOT, "baseline", "snarkjs_baseline.mjs"), d, "--reps", str(steps)]
+        if nm:
+            cmd += ["--node-modules", nm]
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=3000)
+        try:
+            res = json.loads(r.stdout.strip().splitlines()[-1])
+        except Exception:
+            return None
+    if "unavailable" in res or "value" not in res:
+        return None
+    value = res["value"]
+    return {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": 1, "ms_per_step": 1000.0 / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32 limbs (ffjavascript WASM)", "data": "synthetic",
+            "config": {"workload": "nzcp_live snarkjs.plonk.prove (witness given), domain 2^21, 1 proof per step", "domain_log2": 21},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": res.get("cores"), "kind": "snarkjs",
+                             "sample": f"{steps} snarkjs.plonk.prove calls on the zkey / wtns this repository wrote",
+                             "proof_json_bytes_equal": res.get("proof_json_bytes_equal"),
+                             "snarkjs_verifies_our_proof": res.get("snarkjs_verifies_our_proof"), "detail": res},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
 def run_reference(args, rank, world):
-    """--impl reference: the CPU stand-in for `circom WASM witness + snarkjs plonk.prove`, all host threads."""
+    """--impl reference: snarkjs on Node when it exists on the box (baseline/snarkjs_baseline.mjs, kind "snarkjs");
+    otherwise the CPU stand-in for `circom WASM witness + snarkjs plonk.prove` (the C port of the oracle, all host
+    threads, kind "port")."""
     if rank != 0:
         return 0
     try:
@@ -107,6 +171,12 @@ def run_reference(args, rank, world):
     # key material is prepared once with the GPU `plonk setup` (preparation, untimed); the timed path is CPU only
     pr = NzcpProver(live=True, tau=default_tau(), ctx=Context(int(os.environ.get("LOCAL_RANK", "0"))))
     zkey = pr.setup(keep_zkey=True)
+    sj = _snarkjs_available()
+    if sj:
+        line = run_reference_snarkjs(args, sj[0], sj[1], pr, zkey)
+        if line:
+            print(json.dumps(line), flush=True)
+            return 0
     cores = C.use_all_cores()
     steps = args.steps if args.steps is not None else 2
     warm = args.warmup if args.warmup is not None else 1

@@ -44,6 +44,10 @@ extern "C" {
 #define NZCB_E_DIVIDE (-5)    /* "T Polynomial is not divisible" / "Polinomial does not divide" */
 #define NZCB_E_ASSERT (-6)    /* witness program: "Assert Failed" (circom_runtime error 4) */
 #define NZCB_E_NOMEM (-7)
+/* circom_runtime's input errors (witness_calculator.js exception codes): 1 "Signal not found",
+ * 2 "Too many signals set", 3 "Signal already set", 6 "Input signal array access exceeds the size"; 7 = the JS
+ * wrapper's "Not all inputs have been set" */
+#define NZCB_E_SIGNAL(code) (-(100 + (code)))
 
 typedef struct nzcb_ctx nzcb_ctx;
 typedef struct nzcb_zkey nzcb_zkey;
@@ -175,6 +179,25 @@ int32_t nzcb_circuit_info(const nzcb_circuit* c, uint32_t* n_witness, uint32_t* 
  * pass never fails the batch, test/quinSelector.js:66 semantics). */
 int32_t nzcb_witness_batch(nzcb_ctx* ctx, const nzcb_circuit* c, const uint8_t* inputs_le, size_t B,
                            uint8_t* wtns_out, int32_t* status);
+
+/* circom_runtime's input contract in front of nzcb_witness_batch (what `cir.calculateWitness({name: value, ...})`
+ * does before any constraint runs, test/nzcp.js:42; un-vendored circom_runtime, /root/reference/yarn.lock:2496):
+ * signals are addressed by the FNV-1a-64 hash of their name, array values flattened row-major.
+ * `sym` is the circuit's input table (<name>.sym written by `python -m nzcb_circom_b200.circom`): "NZSY", u32 1,
+ * u32 nSignals, u32 nInputs, nSignals x {u64 hash, u32 offset, u32 size}.  hashes[k] / counts[k] name the k-th
+ * provided signal and how many values follow for it in values_le (32 B LE each, taken mod r like Fr.e).
+ * Returns 0 and the nInputs x 32 B buffer nzcb_witness_batch takes, or NZCB_E_SIGNAL(code) with circom_runtime's
+ * message in err.  Host only: no context, no GPU. */
+uint64_t nzcb_fnv1a64(const char* name, size_t len);
+int32_t nzcb_inputs_resolve(const uint8_t* sym, size_t sym_len, uint32_t n_signals, const uint64_t* hashes,
+                            const uint32_t* counts, const uint8_t* values_le, uint8_t* inputs_out, char* err,
+                            size_t err_len);
+/* witness values (nWitness x 32 B LE canonical, as nzcb_witness_batch returns them) -> .wtns v2 file bytes
+ * (snarkjs wtns.calculate's output; *len in = capacity, out = size; out == NULL: query the size).  Host only. */
+int32_t nzcb_wtns_export(const uint8_t* witness_le, uint32_t n_witness, uint8_t* out, size_t* len);
+/* `snarkjs zkey export verificationkey circuit.zkey verification_key.json` (/root/reference/Makefile:56,61):
+ * the JSON text, JSON.stringify(vk, null, 1) layout, from the zkey header alone.  Host only. */
+int32_t nzcb_vkey_to_json(const uint8_t* zkey, size_t zkey_len, char* buf, size_t* len);
 
 /* The same for batches too large to bring every wire back (BASELINE.json configs[3]: 65,536 passes x 26 MB):
  * outputs_le (may be NULL) receives w[1 .. nOutputs] of every pass (B x nOutputs x 32 B LE), i.e. what

@@ -27,20 +27,42 @@ const proofToBytes = (p) => Buffer.concat([
   ...EVALS.map((k) => be32(p[k]))]);
 const publicsOf = (buf) => { const out = []; for (let o = 0; o < buf.length; o += 32) out.push(fromLe(buf, o).toString()); return out; };
 
-// circom_tester.wasm(circomFile): `compiled` maps a circuit name to its witness program (the builder's output)
-exports.wasm = async (circomFile, compiled) => {
-  const art = compiled(circomFile); // { wprog: Buffer, inputOrder: [signal names in declaration order] }
-  const c = n.loadCircuit(art.wprog);
-  const marshal = (input) => Buffer.concat(art.inputOrder.flatMap((name) => flatten(input[name], [])));
+// circom_tester.wasm(circomFile): the circuit is resolved BY FILE NAME, as test/nzcp.js:104,118,347 pass it
+// (`${__dirname}/../circuits/nzcp_live.circom`): <buildDir>/<basename>.{wprog,sym,json} written by
+// `python -m nzcb_circom_b200.circom --all -o <buildDir>` (the role of circom's own --wasm --sym outputs).
+// buildDir: options.buildDir, $NZCB_CIRCUITS or ./circuits_build next to this file.
+const path = require("path");
+const fnv1a64 = (str) => { let h = 0xCBF29CE484222325n; for (const c of Buffer.from(str, "utf8")) { h ^= BigInt(c); h = (h * 0x100000001B3n) & 0xFFFFFFFFFFFFFFFFn; } return h; };
+exports.wasm = async (circomFile, options) => {
+  const dir = (options && options.buildDir) || process.env.NZCB_CIRCUITS || path.join(__dirname, "circuits_build");
+  const base = path.join(dir, path.basename(circomFile, ".circom"));
+  const meta = JSON.parse(fs.readFileSync(base + ".json", "utf8"));
+  const sym = fs.readFileSync(base + ".sym");
+  const c = n.loadCircuit(fs.readFileSync(base + ".wprog"));
+  // circom_runtime's _doCalculateWitness: every key of `input`, hashed, values flattened row-major; the errors
+  // ("Signal not found", "Too many signals set", "Signal already set", "Input signal array access exceeds the size",
+  // "Not all inputs have been set...") come from the library (nzcb_inputs_resolve)
+  const marshal = (input) => {
+    const names = Object.keys(input);
+    const hashes = Buffer.alloc(8 * names.length), counts = Buffer.alloc(4 * names.length), vals = [];
+    names.forEach((k, i) => { const f = flatten(input[k], []); hashes.writeBigUInt64LE(fnv1a64(k), 8 * i); counts.writeUInt32LE(f.length, 4 * i); vals.push(...f); });
+    return n.resolveInputs(sym, hashes, counts, Buffer.concat(vals), meta.nInputs);
+  };
   return {
-    circuit: c, marshal,
+    circuit: c, marshal, meta,
     async calculateWitness(input, sanityCheck) {
       const { witness, status } = n.calculateWitness(c, marshal(input), 1);
       if (sanityCheck !== false && status.readInt32LE(0) !== 0) throw new Error("Error: Assert Failed.");
       const w = []; for (let o = 0; o < witness.length; o += 32) w.push(fromLe(witness, o)); return w;
     },
+    async calculateWTNSBin(input, sanityCheck) { // circom_runtime's name: the .wtns file bytes
+      const { witness, status } = n.calculateWitness(c, marshal(input), 1);
+      if (sanityCheck !== false && status.readInt32LE(0) !== 0) throw new Error("Error: Assert Failed.");
+      return n.wtnsExport(witness);
+    },
   };
 };
+exports.zKey = { async exportVerificationKey(zkeyFile) { return JSON.parse(n.vkeyToJson(typeof zkeyFile === "string" ? fs.readFileSync(zkeyFile) : Buffer.from(zkeyFile.data))); } };
 
 exports.plonk = {
   async prove(zkeyFile, wtnsFile) { // snarkjs.plonk.prove(zkeyFileName, witnessFileName)

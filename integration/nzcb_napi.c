@@ -250,11 +250,57 @@ static napi_value ToBeSigned(napi_env env, napi_callback_info info) {
     return out;
 }
 
+/* resolveInputs(Buffer sym, Buffer hashes(u64 x n), Buffer counts(u32 x n), Buffer values(32 B LE each), nInputs)
+ * -> Buffer inputs (nInputs x 32): circom_runtime's setInputSignal loop; throws its messages ("Signal not found", ...) */
+static napi_value ResolveInputs(napi_env env, napi_callback_info info) {
+    size_t argc = 5; napi_value argv[5]; uint8_t *sym, *values, *outbuf; uint64_t* hashes; uint32_t* counts;
+    size_t slen, hlen, clen, vlen, i, total = 0; uint32_t n_in; napi_value out; char err[128]; int32_t rc;
+    NAPI_OK(napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+    NAPI_OK(napi_get_buffer_info(env, argv[0], (void**)&sym, &slen));
+    NAPI_OK(napi_get_buffer_info(env, argv[1], (void**)&hashes, &hlen));
+    NAPI_OK(napi_get_buffer_info(env, argv[2], (void**)&counts, &clen));
+    NAPI_OK(napi_get_buffer_info(env, argv[3], (void**)&values, &vlen));
+    NAPI_OK(napi_get_value_uint32(env, argv[4], &n_in));
+    if (hlen % 8 || clen != hlen / 2) { napi_throw_error(env, NULL, "nzcb: hashes / counts length mismatch"); return NULL; }
+    for (i = 0; i < clen / 4; i++) total += counts[i];
+    if (vlen != total * 32) { napi_throw_error(env, NULL, "nzcb: values must hold 32 bytes per provided value"); return NULL; }
+    NAPI_OK(napi_create_buffer(env, (size_t)n_in * 32, (void**)&outbuf, &out));
+    rc = nzcb_inputs_resolve(sym, slen, (uint32_t)(hlen / 8), hashes, counts, values, outbuf, err, sizeof err);
+    if (rc != 0) { napi_throw_error(env, NULL, err); return NULL; }
+    return out;
+}
+
+/* wtnsExport(Buffer witness(n x 32 LE)) -> Buffer: the .wtns file snarkjs wtns.calculate writes */
+static napi_value WtnsExport(napi_env env, napi_callback_info info) {
+    size_t argc = 1; napi_value argv[1]; uint8_t *w, *outbuf; size_t wlen, n = 0; napi_value out;
+    NAPI_OK(napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+    NAPI_OK(napi_get_buffer_info(env, argv[0], (void**)&w, &wlen));
+    if (wlen % 32) { napi_throw_error(env, NULL, "nzcb: a witness is n x 32 bytes"); return NULL; }
+    nzcb_wtns_export(w, (uint32_t)(wlen / 32), NULL, &n);
+    NAPI_OK(napi_create_buffer(env, n, (void**)&outbuf, &out));
+    if (nzcb_wtns_export(w, (uint32_t)(wlen / 32), outbuf, &n) != 0) { napi_throw_error(env, NULL, "nzcb: wtns export failed"); return NULL; }
+    return out;
+}
+
+/* vkeyToJson(Buffer zkey) -> string: `snarkjs zkey export verificationkey` (Makefile:56,61) */
+static napi_value VkeyToJson(napi_env env, napi_callback_info info) {
+    size_t argc = 1; napi_value argv[1]; uint8_t* zk; size_t zlen, n = 0; char* buf; napi_value out;
+    NAPI_OK(napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+    NAPI_OK(napi_get_buffer_info(env, argv[0], (void**)&zk, &zlen));
+    if (nzcb_vkey_to_json(zk, zlen, NULL, &n) != 0) { napi_throw_error(env, NULL, "nzcb: not a PLONK zkey"); return NULL; }
+    buf = (char*)malloc(n);
+    if (!buf || nzcb_vkey_to_json(zk, zlen, buf, &n) != 0) { free(buf); napi_throw_error(env, NULL, "nzcb: vkey_to_json failed"); return NULL; }
+    NAPI_OK(napi_create_string_utf8(env, buf, strlen(buf), &out));
+    free(buf);
+    return out;
+}
+
 static napi_value Init(napi_env env, napi_value exports) {
     static const struct { const char* name; napi_callback fn; } fns[] = {
         {"loadZkey", LoadZkey}, {"loadCircuit", LoadCircuit}, {"loadVkey", LoadVkey}, {"prove", Prove},
         {"calculateWitness", CalculateWitness}, {"fullProveBatch", FullProveBatch}, {"fullProveURIs", FullProveURIs},
-        {"verify", Verify}, {"proofToJson", ProofToJson}, {"toBeSigned", ToBeSigned}};
+        {"verify", Verify}, {"proofToJson", ProofToJson}, {"toBeSigned", ToBeSigned}, {"resolveInputs", ResolveInputs},
+        {"wtnsExport", WtnsExport}, {"vkeyToJson", VkeyToJson}};
     size_t i;
     if (nzcb_ctx_create(0, &g_ctx) != 0) {
         napi_throw_error(env, NULL, nzcb_last_error(NULL));  /* "no CUDA device available ...; there is no CPU fallback" */

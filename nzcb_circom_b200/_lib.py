@@ -73,6 +73,10 @@ SIGNATURES = {
     "nzcb_circuit_free": (None, [_vp]),
     "nzcb_circuit_info": (_i32, [_vp] + [ctypes.POINTER(_u32)] * 3),
     "nzcb_witness_batch": (_i32, [_vp, _vp, _vp, _sz, _vp, _vp]),
+    "nzcb_fnv1a64": (ctypes.c_uint64, [_cp, _sz]),
+    "nzcb_inputs_resolve": (_i32, [_vp, _sz, _u32, _vp, _vp, _vp, _vp, _vp, _sz]),
+    "nzcb_wtns_export": (_i32, [_vp, _u32, _vp, ctypes.POINTER(_sz)]),
+    "nzcb_vkey_to_json": (_i32, [_vp, _sz, _vp, ctypes.POINTER(_sz)]),
     "nzcb_witness_batch_ex": (_i32, [_vp, _vp, _vp, _sz, _vp, _vp, _sz, _vp, _vp]),
     "nzcb_plonk_fullprove_batch": (_i32, [_vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp]),
     "nzcb_plonk_fullprove_batch_dev": (_i32, [_vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp]),

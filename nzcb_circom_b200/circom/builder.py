@@ -156,7 +156,7 @@ class Circuit:
         self.constraints = []     # (A, B, C) dicts
         self.prog = []            # instruction tuples
         self.output_assigned = set()
-        self.drop_implied = os.environ.get("NZCB_WITNESS_DROP_IMPLIED") == "1"  # see assert_zero
+        self.drop_implied = os.environ.get("NZCB_WITNESS_DROP_IMPLIED", "1") != "0"  # see assert_zero
 
     # ---- declaration -------------------------------------------------
     @staticmethod
@@ -288,8 +288,9 @@ class Circuit:
         """x === 0 (constraint + run-time assert, circom_runtime error 4 "Assert Failed").
         implied=True marks a check that holds by construction of the witness program itself -- the booleanity of
         bits a decomposition instruction has just written, `in * out === 0` of IsZero after its inverse hint: it
-        stays a constraint of the R1CS, and with NZCB_WITNESS_DROP_IMPLIED=1 it costs no run-time instruction (it
-        can never fire).  Off by default until the slimmer program has been through the GPU parity suite."""
+        stays a constraint of the R1CS and costs no run-time instruction (it can never fire).  On by default since the
+        slimmer program went through the whole GPU parity suite (round 2: 139 tests, witnesses == C oracle);
+        NZCB_WITNESS_DROP_IMPLIED=0 emits the checks again."""
         if isinstance(x, Quad) and not (x.a.is_const() or x.b.is_const()):
             a, b, c = x.a, x.b, -x.c
         else:
@@ -570,6 +571,28 @@ class Artifact:
 
     def flatten_input(self, inp: dict):
         return flatten_input(self.inputs, inp)
+
+    def sym_bytes(self):
+        """the circuit's input table for nzcb_inputs_resolve (include/nzcb.h): circom_runtime addresses main's input
+        signals by the FNV-1a-64 hash of their name; offsets are flattened declaration order"""
+        return sym_bytes(self.inputs)
+
+
+def fnv1a64(name: str) -> int:
+    h = 0xCBF29CE484222325
+    for ch in name.encode():
+        h = ((h ^ ch) * 0x100000001B3) & 0xFFFFFFFFFFFFFFFF
+    return h
+
+
+def sym_bytes(inputs):
+    import struct
+    out, off = b"", 0
+    for name, dims, _first in inputs:
+        n = Circuit._size(dims)
+        out += struct.pack("<QII", fnv1a64(name), off, n)
+        off += n
+    return b"NZSY" + struct.pack("<III", 1, len(inputs), off) + out
 
 
 # ---- input marshalling (circom_runtime: names, arrays flattened row-major) --

@@ -134,7 +134,7 @@ def compile_circuit(name, use_cache=True):
     key = _ALIAS.get(key, key)
     if key not in MAINS:
         raise FileNotFoundError(f"no main component known for {name}")
-    variant = "-di" if os.environ.get("NZCB_WITNESS_DROP_IMPLIED") == "1" else ""  # builder.Circuit.assert_zero
+    variant = "-di" if os.environ.get("NZCB_WITNESS_DROP_IMPLIED", "1") != "0" else ""  # builder.Circuit.assert_zero
     ckey = key + variant
     if ckey in _compiled:
         return _compiled[ckey]
