@@ -342,6 +342,49 @@ def main():
                   "proofs_per_s_device": len(big) / (ctx.last_device_ms / 1000.0),
                   "proofs_per_s_e2e": len(big) / v_wall}
 
+    # ---- SURVEY.md 8d defines a roofline for the NTT and for the witness program too: both measured here, alone
+    roofline_ntt = roofline_witness = None
+    if rank == 0:
+        import ctypes as _ct
+        import numpy as _np
+        ntt = {}
+        for log_n in (21, 23):                       # the prover's two transform sizes (n and 4n)
+            n_el = 1 << log_n
+            d = ctx.dev_alloc(n_el * 32)
+            raw = _np.random.default_rng(log_n).integers(0, 1 << 32, size=(n_el, 8), dtype=_np.uint32)
+            raw[:, 7] &= 0x0FFFFFFF                   # < r
+            ctx.dev_upload(d, raw.tobytes())
+            ts = []
+            for _ in range(6):
+                ctx.check(ctx.lib.nzcb_ntt_fr_dev(ctx.h, d, log_n, 0))
+                ts.append(ctx.last_device_ms)
+            ctx.dev_free(d)
+            ms = sorted(ts[1:])[len(ts[1:]) // 2]
+            imad = 132.0 * n_el * log_n / (ms / 1000.0)
+            ntt[f"2^{log_n}"] = {"ms": ms, "achieved_TIMAD32_s": imad / 1e12, "frac": imad / imad_peak if imad_peak else None,
+                                 "hbm_GB_s": 64.0 * n_el * ((log_n + 2) // 3) / (ms / 1000.0) / 1e9}
+        roofline_ntt = {"bound": "imad", "kernel": "k_ntt_pass (radix-8 register passes)", "unit": "TIMAD32/s", "peak": imad_peak / 1e12,
+                        "algorithmic_unit": "(N/2) log2 N modmul x 264 IMAD32 (SURVEY.md 8d)", "sizes": ntt,
+                        "frac": ntt["2^23"]["frac"], "achieved": ntt["2^23"]["achieved_TIMAD32_s"],
+                        "note": "one transform alone, device resident, median of 5 after 1 warm-up; hbm_GB_s = 64 N bytes per launch x launches"}
+        # witness program: B passes, status only (the wires stay in HBM); bound = HBM writes of nTotal x 32 B per pass
+        Bw = 1024
+        wbuf = marshalled[0] * (Bw // B) if Bw % B == 0 else marshalled[0]
+        nbw = len(wbuf) // (n_in * 32)
+        st = (_ct.c_int32 * nbw)()
+        hcir = pr.tester._handle(ctx)
+        for _ in range(2):
+            ctx.check(ctx.lib.nzcb_witness_batch_ex(ctx.h, hcir, wbuf, nbw, None, None, 0, None, st))
+        w_ms = ctx.last_device_ms
+        w_bytes = float(pr.art.n_total) * 32 * nbw
+        roofline_witness = {"bound": "hbm", "kernel": "k_witness (level-scheduled witness program)", "unit": "GB/s",
+                            "achieved": w_bytes / (w_ms / 1000.0) / 1e9, "peak": None, "frac": None,
+                            "passes": nbw, "ms": w_ms, "passes_per_s": nbw / (w_ms / 1000.0),
+                            "algorithmic_unit": f"nTotal x 32 B written per pass = {pr.art.n_total * 32} B (SURVEY.md 8d)",
+                            "all_accepted": all(x == 0 for x in st),
+                            "note": "includes the H2D of the marshalled inputs (95 KB per pass); the interpreter is bound by its own "
+                                    "dependent instruction chains, not by bandwidth (DESIGN.md 2)"}
+
     # ---- single-proof latency (B = 1, one lane) with the dominant kernel timed alone on the GPU
     one = pr.marshal_passes(all_passes[0][:1])
     check(pr.prove_raw(one, 1))
@@ -386,26 +429,40 @@ def main():
             hbm_peak = json.load(f).get("hbm_gbs")
     except Exception:
         pass
-    traffic = None
+    # dram__bytes_read.sum + dram__bytes_write.sum of one dense 3-commitment accumulation (all of its kernels) from the
+    # committed `ncu --set full` capture: a profiler figure cannot be taken inside a timed run, so the line names its source
+    traffic = traffic_src = None
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_msm_accum_ncu.json")) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")  # ncu --set full: dram__bytes_read.sum + write.sum
+        with open(os.path.join(ROOT, "profiles", "r02_msm_accum_ncu.json")) as f:
+            tj = json.load(f)
+        traffic, traffic_src = tj.get("dram_bytes_per_launch"), "profiles/r02_msm_accum_ncu.json (" + tj.get("what", "") + ")"
     except Exception:
         pass
+    if roofline_witness is not None and hbm_peak:
+        roofline_witness["peak"] = hbm_peak
+        roofline_witness["frac"] = roofline_witness["achieved"] / hbm_peak
     alone = alone_modmul * 264.0 / (alone_ms / 1000.0) if alone_ms > 0 else 0.0
-    roofline = {"bound": "imad", "kernel": "k_msm_accum (MSM bucket accumulation)", "achieved": achieved / 1e12,
+    # executed work: list entries (incl. the null padding of the halving rounds) x modmul per entry: 7/8 of the additions
+    # happen in the batched-affine rounds (6 modmul + 15/32 for the shared inversion), 1/8 in the XYZZ walk (10 modmul)
+    MUL_PER_ENTRY = 0.875 * (6.0 + 15.0 / 32.0) + 0.125 * 10.0
+    roofline = {"bound": "imad", "kernel": "MSM bucket accumulation: k_aff_forward / k_aff_invert / k_aff_backward x 3 rounds + k_msm_accum",
+                "achieved": achieved / 1e12,
                 "peak": imad_peak / 1e12, "unit": "TIMAD32/s", "frac": achieved / imad_peak if imad_peak else None,
-                "traffic": traffic, "launches": n_launch, "avg_launch_ms": acc_ms / n_launch if n_launch else None,
+                "traffic": traffic, "traffic_source": traffic_src, "launches": n_launch, "avg_launch_ms": acc_ms / n_launch if n_launch else None,
                 "kernel_share_of_step": acc_ms / (dev_ms) if dev_ms else None,
                 "note": "timed region: lanes share the GPU, so an accumulation launch can overlap other lanes' kernels; "
                         "`alone` is the same kernel in a single-proof, single-lane run",
-                "executed": {"what": "bucket additions actually executed x 10 modmul x 264 IMAD32 (round 1 commits in the "
-                                     "Lagrange basis, where most scalars are 0/+-1/bytes, so it executes ~5% of its "
-                                     "algorithmic additions; `achieved` keeps SURVEY.md 8d's fixed algorithmic count)",
-                             "achieved": acc_adds * 2640.0 / (acc_ms / 1000.0) / 1e12 if acc_ms > 0 else None,
-                             "frac": acc_adds * 2640.0 / (acc_ms / 1000.0) / imad_peak if acc_ms > 0 and imad_peak else None},
+                "executed": {"what": "list entries actually processed x 6.9 modmul (batched-affine rounds 6 + 15/32, XYZZ tail 10) x "
+                                     "264 IMAD32; round 1 commits in the Lagrange basis, where most scalars are 0/+-1/bytes, so it "
+                                     "executes ~5% of its algorithmic additions; `achieved` keeps SURVEY.md 8d's fixed count of "
+                                     "10 modmul per algorithmic addition",
+                             "entries": acc_adds, "modmul_per_entry": MUL_PER_ENTRY,
+                             "achieved": acc_adds * MUL_PER_ENTRY * 264.0 / (acc_ms / 1000.0) / 1e12 if acc_ms > 0 else None,
+                             "frac": acc_adds * MUL_PER_ENTRY * 264.0 / (acc_ms / 1000.0) / imad_peak if acc_ms > 0 and imad_peak else None,
+                             "additions_per_s": acc_adds / (acc_ms / 1000.0) if acc_ms > 0 else None},
                 "alone": {"achieved": alone / 1e12, "frac": alone / imad_peak if imad_peak else None, "launches": n_alone,
-                          "executed_frac": alone_adds * 2640.0 / (alone_ms / 1000.0) / imad_peak if alone_ms > 0 and imad_peak else None,
+                          "executed_frac": alone_adds * MUL_PER_ENTRY * 264.0 / (alone_ms / 1000.0) / imad_peak if alone_ms > 0 and imad_peak else None,
+                          "additions_per_s": alone_adds / (alone_ms / 1000.0) if alone_ms > 0 else None,
                           "avg_launch_ms": alone_ms / n_alone if n_alone else None,
                           "kernel_share_of_proof": alone_ms / alone_dev_ms if alone_dev_ms else None},
                 "algorithmic_unit": "160 modmul per MSM point x 264 IMAD32 per modmul (SURVEY.md 8d)",
@@ -432,7 +489,8 @@ def main():
                                    "d2h_bytes_per_step": B * (800 + 96 + 4), "same_public_signals_as_e2e": same_publics,
                                    "what": "pass URIs in, proofs out: ingest (base32, COSE, ToBeSigned, marshalling) on the device"},
             "verify": verify,
-            "gpu_launches": int(gpu_launches), "clocks": clocks, "roofline": roofline, "whole_proof_roofline": whole,
+            "gpu_launches": int(gpu_launches), "clocks": clocks, "roofline": roofline, "roofline_ntt": roofline_ntt,
+            "roofline_witness": roofline_witness, "whole_proof_roofline": whole,
             "latency_ms_single_proof": latency_ms,
             "latency_ms_single_proof_msm_split": split_latency_ms, "msm_split_proof_equals_single_gpu": split_equal,
             "wall_s_device_leg": wall_dev,

@@ -30,7 +30,7 @@ def main(argv=None):
     for name in names:
         key = os.path.splitext(os.path.basename(name))[0]
         art = compile_circuit(key)
-        for ext, data in ((".r1cs", art.r1cs_bytes()), (".wprog", art.wprog_bytes()), (".sym", art.sym_bytes())):
+        for ext, data in ((".r1cs", art.r1cs_bytes()), (".wprog", art.wprog_bytes(native=True)), (".sym", art.sym_bytes())):
             with open(os.path.join(a.out, key + ext), "wb") as f:
                 f.write(data)
         meta = {"main": key, "nWitness": art.n_witness, "nOutputs": art.n_out, "nInputs": art.n_in,

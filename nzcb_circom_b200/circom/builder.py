@@ -22,6 +22,11 @@ import struct
 R = 0x30644e72e131a029b85045b68181585d2833e84879b9709143e1f593f0000001
 
 OP_LIN, OP_MUL, OP_BITS, OP_INV, OP_ASSERT, OP_BITSLC = 1, 2, 3, 4, 5, 6
+# Word-level ("fat") instructions of the NATIVE witness program (csrc/witness.cu): one SHA-2 round / one message
+# schedule step computed on 32- or 64-bit words, every bit wire of the step written out afterwards.  They replace
+# the generic instructions the same step emits (kept alongside: the oracle's program is the generic one, so the
+# oracle VM checks the native semantics wire for wire).  Signals, numbering and R1CS are untouched.
+OP_SHAROUND, OP_SHASCHED = 7, 8
 
 
 class LC:
@@ -309,6 +314,13 @@ class Circuit:
     def assert_eq(self, x, y):
         self.assert_zero(x - y)
 
+    def fuse(self, p0, op, payload):
+        """the instructions emitted since prog index p0 can be replaced, in the native program, by ONE word-level
+        instruction (op, payload); the generic ones are kept for the generic (oracle) program"""
+        generic = self.prog[p0:]
+        del self.prog[p0:]
+        self.prog.append((op, payload, generic))
+
     # ---- outputs -------------------------------------------------------
     def finalize(self):
         assert len(self.output_assigned) == self.n_out, f"{self.name}: unassigned main outputs"
@@ -385,9 +397,13 @@ class MulSumChain:
 
 
 class Compiled:
-    """Finalised circuit: R1CS + witness program with temps remapped and levels computed."""
+    """Finalised circuit: R1CS + witness program with temps remapped and levels computed.  native=True keeps the
+    word-level instructions (the GPU's program); native=False expands them into the generic instructions they stand
+    for (the oracle's program).  Both write the same wires."""
 
-    def __init__(self, c: Circuit):
+    def __init__(self, c: Circuit, native=False):
+        self.native = native
+        self._c = c
         self.name = c.name
         self.n_witness = c.n_wires
         self.n_total = c.n_wires + c.n_temps
@@ -407,9 +423,22 @@ class Compiled:
         level = [0] * self.n_total
         prog = []
         lv = []
+        flat = []
         for ins in c.prog:
+            if ins[0] in (OP_SHAROUND, OP_SHASCHED) and not native:
+                flat.extend(ins[2])
+            else:
+                flat.append(ins)
+        for ins in flat:
             op = ins[0]
-            if op == OP_LIN:
+            if op in (OP_SHAROUND, OP_SHASCHED):
+                pl = dict(ins[1])
+                pl["words"] = [[rlc(b) for b in word] for word in pl["words"]]
+                l = 1 + max((level[w] for word in pl["words"] for b in word for w in b.t), default=0)
+                for w in range(pl["w0"], pl["w0"] + pl["size"]):
+                    level[w] = l
+                prog.append((op, pl))
+            elif op == OP_LIN:
                 lc = rlc(ins[2])
                 dst = rid(ins[1])
                 l = 1 + max((level[w] for w in lc.t), default=0)
@@ -490,6 +519,11 @@ class Compiled:
            INV    op, dst, src
            ASSERT op, <lc a>, <lc b>, <lc c>
            BITSLC op, dst0, n, <lc>          (bits of the value of an LC)
+           SHAROUND op, n, r1a r1b r1c (Sigma1), r0a r0b r0c (Sigma0), K_lo, K_hi, w0, size, 9 n x <bit>, <lc>...
+                     (bits of a b c d e f g h w, LSB first)        -- native program only
+           SHASCHED op, n, r1a r1b r1c (sigma1, r1c a shift), r0a r0b r0c (sigma0), w0, size, 4 n x <bit>, <lc>...
+                     (bits of w[t-2], w[t-7], w[t-15], w[t-16])    -- native program only
+           <bit> = wire id, or 0x80000000 | offset (from the instruction's first word) of the <lc> giving the bit
            <lc> = n_terms, const_idx (0xffffffff = no constant), then n_terms x (wire, coef_idx)"""
         consts = {1: 0, R - 1: 1}
         clist = [1, R - 1]
@@ -515,7 +549,26 @@ class Compiled:
             ioff.append(len(code))
             op = ins[0]
             code.append(op)
-            if op == OP_LIN:
+            if op in (OP_SHAROUND, OP_SHASCHED):
+                pl = ins[1]
+                code.append(pl["n"])
+                code.extend(pl["rot1"])
+                code.extend(pl["rot0"])
+                if op == OP_SHAROUND:
+                    code.extend((pl["K"] & 0xFFFFFFFF, pl["K"] >> 32))
+                code.extend((pl["w0"], pl["size"]))
+                start = ioff[-1]
+                refs = len(code)
+                bits = [b for word in pl["words"] for b in word]
+                code.extend([0] * len(bits))
+                for k, b in enumerate(bits):
+                    w = b.single_wire()
+                    if w is not None:
+                        code[refs + k] = w
+                    else:
+                        code[refs + k] = 0x80000000 | (len(code) - start)
+                        emit_lc(b)
+            elif op == OP_LIN:
                 code.append(ins[1])
                 emit_lc(ins[2])
             elif op == OP_MUL:
@@ -546,10 +599,17 @@ class Compiled:
                 np.asarray(starts, dtype="<u4").tobytes() + np.asarray(code, dtype="<u4").tobytes())
 
     def artifact(self):
-        """the build products a circom run leaves on disk: .r1cs, witness program, I/O table"""
-        return Artifact(self.name, self.n_witness, self.n_total, self.n_out, self.n_in, list(self.inputs),
-                        list(self.outputs), len(self.constraints), self.n_levels, len(self.prog), self.wprog_bytes(),
-                        self.r1cs_bytes())
+        """the build products a circom run leaves on disk: .r1cs, witness program (generic, and the native one the
+        GPU loads when the circuit has word-level steps), I/O table"""
+        art = Artifact(self.name, self.n_witness, self.n_total, self.n_out, self.n_in, list(self.inputs),
+                       list(self.outputs), len(self.constraints), self.n_levels, len(self.prog), self.wprog_bytes(),
+                       self.r1cs_bytes())
+        if not self.native and os.environ.get("NZCB_WITNESS_NATIVE_SHA", "1") != "0" and \
+                any(i[0] in (OP_SHAROUND, OP_SHASCHED) for i in self._c.prog):
+            nat = Compiled(self._c, native=True)
+            art.wprog_native = nat.wprog_bytes()
+            art.n_levels_native, art.n_instr_native = nat.n_levels, len(nat.prog)
+        return art
 
     def flatten_input(self, inp: dict):
         return flatten_input(self.inputs, inp)
@@ -563,7 +623,11 @@ class Artifact:
         self.n_constraints, self.n_levels, self.n_instr = n_constraints, n_levels, n_instr
         self.wprog, self.r1cs = wprog, r1cs
 
-    def wprog_bytes(self):
+    def wprog_bytes(self, native=False):
+        """the witness program: generic (what the oracle VMs run; always present) or, native=True, the one with
+        word-level SHA-2 steps that the GPU loads (falls back to the generic one when the circuit has none)"""
+        if native:
+            return getattr(self, "wprog_native", None) or self.wprog
         return self.wprog
 
     def r1cs_bytes(self):

@@ -9,11 +9,11 @@ byte, standard FIPS 180-4 padding, done in-circuit for the variable length.  The
 gadgets below are restated in the circomlib style (Xor3 / Ch / Maj per bit,
 BinSum for the modular additions) so constraint counts are comparable with the
 real thing; the round constants are derived from first principles (fractional
-parts of square / cube roots of primes) and pinned by the hashlib cross-checks in
-tests/test_witness_oracle.py."""
+parts of square / cube roots of primes) and pinned by the hashlib cross-checks of
+tests/test_nzcp.py (the digests of real and synthetic passes) and tests/test_sha_native.py."""
 from math import isqrt
 
-from .builder import LC, Circuit
+from .builder import LC, OP_SHAROUND, OP_SHASCHED, Circuit
 from .circomlib import is_equal, num2bits
 
 
@@ -117,15 +117,40 @@ class _Sha2:
         return [_xor3(c, a[i], b[i], third[i]) for i in range(self.n)]
 
     def compress(self, c: Circuit, state, block_words):
-        """state: 8 words; block_words: 16 words (LSB-first bit lists).  Returns the new state."""
+        """state: 8 words; block_words: 16 words (LSB-first bit lists).  Returns the new state.
+
+        Every message-schedule step and every round whose wires come out in the regular layout (no constant
+        folding: all state bits are signals) is ALSO recorded as one word-level instruction of the native witness
+        program (builder.OP_SHASCHED / OP_SHAROUND): the same wires, computed on n-bit words."""
         n = self.n
         w = list(block_words)
+        r3_1, r3_0 = self.small1[2], self.small0[2]
         for t in range(16, self.rounds):
+            p0, w0 = len(c.prog), c.n_wires
             s1 = self._sigma(c, w[t - 2], self.small1)
             s0 = self._sigma(c, w[t - 15], self.small0)
-            w.append(_binsum(c, n, [s1, w[t - 7], s0, w[t - 16]]))
+            wt = _binsum(c, n, [s1, w[t - 7], s0, w[t - 16]])
+            w.append(wt)
+            # layout of a regular step: sigma1 (mid, out interleaved; out only where the shifted operand is 0),
+            # sigma0 likewise, then the n + 2 sum bits
+            o_s0 = 2 * n - r3_1
+            o_w = o_s0 + 2 * n - r3_0
+            size = o_w + n + 2
+
+            def sig_out(off, r3, i):
+                return w0 + off + (2 * i + 1 if i < n - r3 else 2 * (n - r3) + i - (n - r3))
+
+            regular = (c.n_wires - w0 == size and
+                       all(s1[i].single_wire() == sig_out(0, r3_1, i) for i in range(n)) and
+                       all(s0[i].single_wire() == sig_out(o_s0, r3_0, i) for i in range(n)) and
+                       all(wt[i].single_wire() == w0 + o_w + i for i in range(n)))
+            if regular:
+                c.fuse(p0, OP_SHASCHED, {"n": n, "rot1": list(self.small1[:3]), "rot0": list(self.small0[:3]), "w0": w0,
+                                         "size": size, "words": [w[t - 2], w[t - 7], w[t - 15], w[t - 16]]})
         a, b, cc, d, e, f, g, h = state
         for t in range(self.rounds):
+            p0, w0 = len(c.prog), c.n_wires
+            ins = [a, b, cc, d, e, f, g, h, w[t]]
             S1 = self._sigma(c, e, self.big1)
             chv = [_ch(c, e[i], f[i], g[i]) for i in range(n)]
             t1 = _binsum(c, n, [h, S1, chv, _const_word(self.K[t], n), w[t]])
@@ -136,6 +161,18 @@ class _Sha2:
             e = _binsum(c, n, [d, t1])
             d, cc, b = cc, b, a
             a = _binsum(c, n, [t1, t2])
+            # regular layout: S1 2n | ch n | t1 n+3 | S0 2n | maj 2n | t2 n+1 | e n+1 | a n+1   (11 n + 6 wires)
+            o_ch, o_t1, o_S0, o_mj, o_t2, o_e, o_a = 2 * n, 3 * n, 4 * n + 3, 6 * n + 3, 8 * n + 3, 9 * n + 4, 10 * n + 5
+            size = 11 * n + 6
+            regular = (c.n_wires - w0 == size and
+                       all(x.single_wire() is not None for word in ins[:8] for x in word) and
+                       all(S1[i].single_wire() == w0 + 2 * i + 1 and chv[i].single_wire() == w0 + o_ch + i and
+                           t1[i].single_wire() == w0 + o_t1 + i and S0[i].single_wire() == w0 + o_S0 + 2 * i + 1 and
+                           mj[i].single_wire() == w0 + o_mj + 2 * i + 1 and t2[i].single_wire() == w0 + o_t2 + i and
+                           e[i].single_wire() == w0 + o_e + i and a[i].single_wire() == w0 + o_a + i for i in range(n)))
+            if regular:
+                c.fuse(p0, OP_SHAROUND, {"n": n, "rot1": list(self.big1[:3]), "rot0": list(self.big0[:3]), "K": self.K[t],
+                                         "w0": w0, "size": size, "words": ins})
         new = [a, b, cc, d, e, f, g, h]
         return [_binsum(c, n, [state[i], new[i]]) for i in range(8)]
 

@@ -178,7 +178,7 @@ class WasmTester:
     def _handle(self, ctx):
         key = id(ctx)
         if key not in self._handles:
-            data = self.wprog
+            data = self.compiled.wprog_bytes(native=True)  # word-level SHA-2 steps where the circuit has them
             buf = (ctypes.c_uint8 * len(data)).from_buffer_copy(data)
             h = ctypes.c_void_p()
             ctx.check(ctx.lib.nzcb_circuit_load(ctx.h, buf, len(data), ctypes.byref(h)))

@@ -22,7 +22,7 @@
 
 using namespace nzcb;
 
-enum { OP_LIN = 1, OP_MUL = 2, OP_BITS = 3, OP_INV = 4, OP_ASSERT = 5, OP_BITSLC = 6 };
+enum { OP_LIN = 1, OP_MUL = 2, OP_BITS = 3, OP_INV = 4, OP_ASSERT = 5, OP_BITSLC = 6, OP_SHAROUND = 7, OP_SHASCHED = 8 };
 constexpr uint32_t NZ_INV_TAB = 1024;
 constexpr uint32_t NZ_LONG_LC = 24;  // an LC (or bit decomposition) longer than this is evaluated by a whole warp
 
@@ -175,9 +175,131 @@ __device__ __forceinline__ Fr inv_or_zero(const ProgView& pv, const Fr& v) {
     return wit_inv(v);
 }
 
+// ---- word-level SHA-2 steps (builder.OP_SHAROUND / OP_SHASCHED; circuits/nzcptpl.circom:509-516 Sha256Var(3),
+// :577-580 Sha512(512)) -----------------------------------------------------------------------------------------
+// One warp per step.  The step's input words are gathered bit by bit (a bit is a wire or a short LC of wires) with
+// warp ballots, the round / schedule step is computed on n-bit words, and every bit wire the circuit has for the step
+// (Xor3's b*c products and outputs, Ch, Maj's product and output, the carry-extended BinSum decompositions) is
+// written at its place: the same wires the generic instructions of the step write (the oracle VM runs those).
+template <class WT>
+struct ShaWord;
+template <>
+struct ShaWord<uint32_t> {
+    static constexpr uint32_t N = 32;
+    typedef uint64_t Wide;
+};
+template <>
+struct ShaWord<uint64_t> {
+    static constexpr uint32_t N = 64;
+    typedef unsigned __int128 Wide;
+};
+
+template <class WT>
+__device__ __forceinline__ WT sha_rotr(WT x, uint32_t r) {
+    constexpr uint32_t N = ShaWord<WT>::N;
+    r &= N - 1;
+    return r ? (WT)((x >> r) | (x << (N - r))) : x;
+}
+__device__ __forceinline__ void sha_put(Fr* __restrict__ W, uint32_t idx, uint32_t bit) {
+    Fr o = Fr::zero();
+    o.v[0] = bit;
+    W[idx] = o;
+}
+// bit `i` of input word `k` of the instruction at p: refs start at `refs`
+__device__ __forceinline__ uint32_t sha_in_bit(const ProgView& pv, const Fr* __restrict__ W, uint32_t p, uint32_t refs,
+                                               uint32_t n, uint32_t k, uint32_t i) {
+    const uint32_t ref = pv.code[refs + k * n + i];
+    if (!(ref & 0x80000000u)) return W[ref].v[0] & 1u;
+    uint32_t q = p + (ref & 0x7fffffffu);
+    const GlobalCode gc{pv.code};
+    return eval_lc(pv, gc, W, q).v[0] & 1u;
+}
+template <class WT, int NW>
+__device__ __forceinline__ void sha_gather(const ProgView& pv, const Fr* __restrict__ W, uint32_t p, uint32_t refs,
+                                           uint32_t lane, WT* word) {
+    constexpr uint32_t N = ShaWord<WT>::N;
+    uint32_t lo[NW], hi[NW];
+#pragma unroll
+    for (int k = 0; k < NW; k++) {
+        lo[k] = sha_in_bit(pv, W, p, refs, N, k, lane);
+        hi[k] = N == 64 ? sha_in_bit(pv, W, p, refs, N, k, lane + 32) : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < NW; k++) {
+        const uint32_t l = __ballot_sync(0xffffffffu, lo[k]);
+        const uint32_t h = N == 64 ? __ballot_sync(0xffffffffu, hi[k]) : 0u;
+        word[k] = (WT)(((uint64_t)h << 32) | l);
+    }
+}
+// Xor3 block: for i < n_mid (mid, out) interleaved, then out only
+template <class WT>
+__device__ __forceinline__ void sha_put_xor3(Fr* __restrict__ W, uint32_t base, WT mid, WT out, uint32_t n_mid, uint32_t lane) {
+    constexpr uint32_t N = ShaWord<WT>::N;
+    for (uint32_t i = lane; i < N; i += 32) {
+        if (i < n_mid) {
+            sha_put(W, base + 2 * i, (uint32_t)((mid >> i) & 1));
+            sha_put(W, base + 2 * i + 1, (uint32_t)((out >> i) & 1));
+        } else {
+            sha_put(W, base + 2 * n_mid + (i - n_mid), (uint32_t)((out >> i) & 1));
+        }
+    }
+}
+template <class WIDE>
+__device__ __forceinline__ void sha_put_bits(Fr* __restrict__ W, uint32_t base, WIDE v, uint32_t count, uint32_t lane) {
+    for (uint32_t j = lane; j < count; j += 32) sha_put(W, base + j, (uint32_t)((v >> j) & 1));
+}
+
+// out of line: the interpreter's own loop is latency bound and must keep its registers.  TAG gives every kernel its
+// own copy (ptxas 12.9 segfaults when two kernels of this translation unit share an out-of-line routine).
+template <class WT, uint32_t TAG>
+__device__ __noinline__ void sha_step_warp(const ProgView& pv, Fr* __restrict__ W, uint32_t p, uint32_t lane, uint32_t op) {
+    constexpr uint32_t N = ShaWord<WT>::N;
+    typedef typename ShaWord<WT>::Wide Wide;
+    const uint32_t r1a = pv.code[p + 2], r1b = pv.code[p + 3], r1c = pv.code[p + 4];
+    const uint32_t r0a = pv.code[p + 5], r0b = pv.code[p + 6], r0c = pv.code[p + 7];
+    if (op == OP_SHAROUND) {
+        const WT K = (WT)(((uint64_t)pv.code[p + 9] << 32) | pv.code[p + 8]);
+        const uint32_t w0 = pv.code[p + 10], refs = p + 12;
+        WT x[9];  // a b c d e f g h w
+        sha_gather<WT, 9>(pv, W, p, refs, lane, x);
+        const WT A = x[0], B = x[1], C = x[2], D = x[3], E = x[4], F = x[5], G = x[6], H = x[7], Wt = x[8];
+        const WT e2 = sha_rotr(E, r1b), e3 = sha_rotr(E, r1c);
+        const WT S1 = sha_rotr(E, r1a) ^ e2 ^ e3;
+        const WT ch = (E & F) ^ (~E & G);
+        const Wide t1 = (Wide)H + S1 + ch + K + Wt;
+        const WT a2 = sha_rotr(A, r0b), a3 = sha_rotr(A, r0c);
+        const WT S0 = sha_rotr(A, r0a) ^ a2 ^ a3;
+        const WT mj = (A & B) ^ (A & C) ^ (B & C);
+        const Wide t2 = (Wide)S0 + mj;
+        const Wide en = (Wide)D + (WT)t1;
+        const Wide an = (Wide)(WT)t1 + (WT)t2;
+        sha_put_xor3<WT>(W, w0, e2 & e3, S1, N, lane);
+        sha_put_bits<WT>(W, w0 + 2 * N, ch, N, lane);
+        sha_put_bits<Wide>(W, w0 + 3 * N, t1, N + 3, lane);
+        sha_put_xor3<WT>(W, w0 + 4 * N + 3, a2 & a3, S0, N, lane);
+        sha_put_xor3<WT>(W, w0 + 6 * N + 3, B & C, mj, N, lane);
+        sha_put_bits<Wide>(W, w0 + 8 * N + 3, t2, N + 1, lane);
+        sha_put_bits<Wide>(W, w0 + 9 * N + 4, en, N + 1, lane);
+        sha_put_bits<Wide>(W, w0 + 10 * N + 5, an, N + 1, lane);
+    } else {
+        const uint32_t w0 = pv.code[p + 8], refs = p + 10;
+        WT x[4];  // w[t-2] w[t-7] w[t-15] w[t-16]
+        sha_gather<WT, 4>(pv, W, p, refs, lane, x);
+        const WT b1 = sha_rotr(x[0], r1b), c1 = (WT)(x[0] >> r1c);
+        const WT s1 = sha_rotr(x[0], r1a) ^ b1 ^ c1;
+        const WT b0 = sha_rotr(x[2], r0b), c0 = (WT)(x[2] >> r0c);
+        const WT s0 = sha_rotr(x[2], r0a) ^ b0 ^ c0;
+        const Wide sum = (Wide)s1 + x[1] + s0 + x[3];
+        const uint32_t o_s0 = 2 * N - r1c, o_w = o_s0 + 2 * N - r0c;
+        sha_put_xor3<WT>(W, w0, b1 & c1, s1, N - r1c, lane);
+        sha_put_xor3<WT>(W, w0 + o_s0, b0 & c0, s0, N - r0c, lane);
+        sha_put_bits<Wide>(W, w0 + o_w, sum, N + 2, lane);
+    }
+}
+
 // Executes the instruction whose words rd() serves from offset p.  WARP: all 32 lanes cooperate on its LCs (lane 0
 // commits; code stream only); else one thread.
-template <bool WARP, class RD>
+template <bool WARP, class RD, uint32_t TAG = 0>
 __device__ __forceinline__ bool exec_instr(const ProgView& pv, const RD& rd, Fr* __restrict__ W, uint32_t p, uint32_t lane) {
     const uint32_t op = rd(p) & 0xffu;
     auto LC = [&](uint32_t& q) { return WARP ? eval_lc_warp(pv, W, q, lane) : eval_lc(pv, rd, W, q); };
@@ -213,6 +335,11 @@ __device__ __forceinline__ bool exec_instr(const ProgView& pv, const RD& rd, Fr*
         }
     } else if (op == OP_INV) {
         if (commit) W[rd(p + 1)] = inv_or_zero(pv, W[rd(p + 2)]);
+    } else if (op == OP_SHAROUND || op == OP_SHASCHED) {  // always scheduled as a one-warp instruction (loader)
+        if (WARP) {
+            if (pv.code[p + 1] == 64) sha_step_warp<uint64_t, TAG>(pv, W, p, lane, op);
+            else sha_step_warp<uint32_t, TAG>(pv, W, p, lane, op);
+        }
     } else {  // OP_ASSERT
         p += 1;
         const Fr a = LC(p);
@@ -314,7 +441,7 @@ __global__ void __launch_bounds__(T, CTAS_PER_SM) k_witness(ProgView pv, const F
             }
             if (hi + nl_n + threadIdx.x < hi_n) prefetch(buf ^ 1, hi + nl_n + threadIdx.x);
             __pipeline_commit();
-            for (uint32_t i = lo + warp; i < lo + nl; i += n_warps) failed |= exec_instr<true>(pv, gcode, W, pv.ioff[i], lane);
+            for (uint32_t i = lo + warp; i < lo + nl; i += n_warps) failed |= exec_instr<true, GlobalCode, T>(pv, gcode, W, pv.ioff[i], lane);
             uint32_t i = lo + nl + threadIdx.x;
             if (i < hi) {
                 __pipeline_wait_prior(1);  // everything but the copy just issued has landed: this level's record
@@ -448,6 +575,27 @@ extern "C" int32_t nzcb_circuit_load(nzcb_ctx* ctx, const uint8_t* data, size_t 
                 ok = p + 3 <= c->n_code && code[p + 1] < c->n_total && code[p + 2] < c->n_total;
             } else if (op == OP_ASSERT) {
                 p += 1; ok = lc_ok(p) && lc_ok(p) && lc_ok(p);
+            } else if (op == OP_SHAROUND || op == OP_SHASCHED) {
+                const uint32_t hdr = op == OP_SHAROUND ? 12u : 10u, nw = op == OP_SHAROUND ? 9u : 4u;
+                ok = (uint64_t)p + hdr <= c->n_code;
+                const uint32_t n = ok ? code[p + 1] : 0;
+                ok = ok && (n == 32 || n == 64) && (uint64_t)p + hdr + (uint64_t)nw * n <= c->n_code;
+                if (ok) {
+                    for (uint32_t k = 2; k < 8; k++) ok = ok && code[p + k] < n;
+                    const uint32_t w0 = code[p + hdr - 2], size = code[p + hdr - 1];
+                    const uint32_t want = op == OP_SHAROUND ? 11 * n + 6 : 5 * n + 2 - code[p + 4] - code[p + 7];
+                    ok = ok && size == want && (uint64_t)w0 + size <= c->n_total;
+                    for (uint32_t k = 0; ok && k < nw * n; k++) {
+                        const uint32_t ref = code[p + hdr + k];
+                        if (ref & 0x80000000u) {
+                            uint32_t q = p + (ref & 0x7fffffffu);
+                            ok = q >= p + hdr + nw * n && lc_ok(q);
+                        } else {
+                            ok = ref < c->n_total;
+                        }
+                    }
+                }
+                cur_weight = 1u << 20;  // one warp, first in its level
             } else ok = false;
             weight[i] = cur_weight;
         }
@@ -475,7 +623,8 @@ extern "C" int32_t nzcb_circuit_load(nzcb_ctx* ctx, const uint8_t* data, size_t 
             const uint32_t p = ioff_sorted[k];
             const uint32_t op = code[p];
             uint32_t len;
-            if (op == OP_BITS) len = 4;
+            if (op == OP_SHAROUND || op == OP_SHASCHED) len = REC_WORDS + 1;  // never a record: runs from the code stream
+            else if (op == OP_BITS) len = 4;
             else if (op == OP_INV) len = 3;
             else if (op == OP_BITSLC) len = 3 + 2 + 2 * code[p + 3];
             else {

@@ -36,8 +36,8 @@ class Program:
         assert pos + 4 * n_code == len(data)
 
 
-def run(prog: Program, inputs, check=True):
-    """inputs: n_in ints in declaration order.  Returns the witness (n_witness ints).
+def run(prog: Program, inputs, check=True, full=False):
+    """inputs: n_in ints in declaration order.  Returns the witness (n_witness ints; full=True: the program temps too).
     Raises AssertFailed when a `===` of the circuit does not hold (sanityCheck = true)."""
     assert len(inputs) == prog.n_in
     w = [0] * prog.n_total
@@ -87,7 +87,7 @@ def run(prog: Program, inputs, check=True):
                 raise AssertFailed("Assert Failed")
         else:
             raise ValueError(f"bad opcode {op}")
-    return w[:prog.n_witness]
+    return w if full else w[:prog.n_witness]
 
 
 def check_r1cs(r1cs_bytes: bytes, witness):
