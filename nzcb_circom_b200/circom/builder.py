@@ -27,6 +27,10 @@ OP_LIN, OP_MUL, OP_BITS, OP_INV, OP_ASSERT, OP_BITSLC = 1, 2, 3, 4, 5, 6
 # the generic instructions the same step emits (kept alongside: the oracle's program is the generic one, so the
 # oracle VM checks the native semantics wire for wire).  Signals, numbering and R1CS are untouched.
 OP_SHAROUND, OP_SHASCHED = 7, 8
+# QuinSelector(N) (circuits/quinSelector.circom:26-41) as one instruction: the N IsZero inverses, the N equality flags
+# and the N running sums written from the index and the one selected input
+OP_QUINSEL = 9
+FAT_OPS = (OP_SHAROUND, OP_SHASCHED, OP_QUINSEL)
 
 
 class LC:
@@ -425,7 +429,7 @@ class Compiled:
         lv = []
         flat = []
         for ins in c.prog:
-            if ins[0] in (OP_SHAROUND, OP_SHASCHED) and not native:
+            if ins[0] in FAT_OPS and not native:
                 flat.extend(ins[2])
             else:
                 flat.append(ins)
@@ -436,6 +440,14 @@ class Compiled:
                 pl["words"] = [[rlc(b) for b in word] for word in pl["words"]]
                 l = 1 + max((level[w] for word in pl["words"] for b in word for w in b.t), default=0)
                 for w in range(pl["w0"], pl["w0"] + pl["size"]):
+                    level[w] = l
+                prog.append((op, pl))
+            elif op == OP_QUINSEL:
+                pl = dict(ins[1])
+                pl["index"] = rlc(pl["index"])
+                pl["ins"] = [rlc(b) for b in pl["ins"]]
+                l = 1 + max((level[w] for b in pl["ins"] + [pl["index"]] for w in b.t), default=0)
+                for w in range(pl["w0"], pl["w0"] + 3 * len(pl["ins"])):
                     level[w] = l
                 prog.append((op, pl))
             elif op == OP_LIN:
@@ -523,7 +535,9 @@ class Compiled:
                      (bits of a b c d e f g h w, LSB first)        -- native program only
            SHASCHED op, n, r1a r1b r1c (sigma1, r1c a shift), r0a r0b r0c (sigma0), w0, size, 4 n x <bit>, <lc>...
                      (bits of w[t-2], w[t-7], w[t-15], w[t-16])    -- native program only
-           <bit> = wire id, or 0x80000000 | offset (from the instruction's first word) of the <lc> giving the bit
+           QUINSEL  op, N, w0, N x <bit> (the inputs), <lc index>, <lc>...  -- native program only; writes
+                     inv_i, eq_i, sum_i at w0 + 3 i
+           <bit> = wire id, or 0x80000000 | offset (from the instruction's first word) of the <lc> giving the value
            <lc> = n_terms, const_idx (0xffffffff = no constant), then n_terms x (wire, coef_idx)"""
         consts = {1: 0, R - 1: 1}
         clist = [1, R - 1]
@@ -549,7 +563,21 @@ class Compiled:
             ioff.append(len(code))
             op = ins[0]
             code.append(op)
-            if op in (OP_SHAROUND, OP_SHASCHED):
+            if op == OP_QUINSEL:
+                pl = ins[1]
+                start = ioff[-1]
+                code.extend((len(pl["ins"]), pl["w0"]))
+                refs = len(code)
+                code.extend([0] * len(pl["ins"]))
+                emit_lc(pl["index"])
+                for k, b in enumerate(pl["ins"]):
+                    w = b.single_wire()
+                    if w is not None:
+                        code[refs + k] = w
+                    else:
+                        code[refs + k] = 0x80000000 | (len(code) - start)
+                        emit_lc(b)
+            elif op in (OP_SHAROUND, OP_SHASCHED):
                 pl = ins[1]
                 code.append(pl["n"])
                 code.extend(pl["rot1"])
@@ -604,8 +632,8 @@ class Compiled:
         art = Artifact(self.name, self.n_witness, self.n_total, self.n_out, self.n_in, list(self.inputs),
                        list(self.outputs), len(self.constraints), self.n_levels, len(self.prog), self.wprog_bytes(),
                        self.r1cs_bytes())
-        if not self.native and os.environ.get("NZCB_WITNESS_NATIVE_SHA", "1") != "0" and \
-                any(i[0] in (OP_SHAROUND, OP_SHASCHED) for i in self._c.prog):
+        if not self.native and os.environ.get("NZCB_WITNESS_NATIVE", "1") != "0" and \
+                any(i[0] in FAT_OPS for i in self._c.prog):
             nat = Compiled(self._c, native=True)
             art.wprog_native = nat.wprog_bytes()
             art.n_levels_native, art.n_instr_native = nat.n_levels, len(nat.prog)

@@ -3,7 +3,7 @@ Each function cites the template it follows in /root/reference/circuits/.
 Signals that the circom source defines by ``<==`` from a *linear* expression are
 carried as LCs (what ``--O2`` leaves after substitution); every quadratic ``<==``
 and every hint is one wire, in source order."""
-from .builder import LC, Circuit
+from .builder import LC, OP_QUINSEL, Circuit
 from .circomlib import (bits2num, calculate_total, is_equal, is_zero, less_than, log2, num2bits, shr)
 
 MAJOR_TYPE_INT = 0
@@ -24,11 +24,21 @@ def quin_selector(c: Circuit, ins, index):
         bits = log2(choices) + 1
         lt = less_than(c, bits, index, choices)          # :19-24
         c.assert_eq(lt, 1)
+    p0, w0 = len(c.prog), c.n_wires
     chain = c.chain()                                     # sums[i] <== eqs[i] * in[i] + sums[i-1]
+    eqs = []
     for i in range(choices):
         eq = is_zero(c, i - index)                        # :32-33
+        eqs.append(eq)
         chain.step(eq, ins[i])                            # :37
-    return chain.finish()                                 # :41  (0 when choices == 0)
+    sums = [w for w, _, _ in chain.steps]
+    out = chain.finish()                                  # :41  (0 when choices == 0)
+    # regular layout (no constant folding): inv_i, eq_i, sum_i at w0 + 3 i -- then the whole selector is also one
+    # word-level instruction of the native witness program
+    if choices > 0 and c.n_wires - w0 == 3 * choices and len(sums) == choices and \
+            all(eqs[i].single_wire() == w0 + 3 * i + 1 and sums[i] == w0 + 3 * i + 2 for i in range(choices)):
+        c.fuse(p0, OP_QUINSEL, {"w0": w0, "index": index, "ins": [LC.of(x) for x in ins]})
+    return out
 
 
 def get_type(c, v):

@@ -22,7 +22,7 @@
 
 using namespace nzcb;
 
-enum { OP_LIN = 1, OP_MUL = 2, OP_BITS = 3, OP_INV = 4, OP_ASSERT = 5, OP_BITSLC = 6, OP_SHAROUND = 7, OP_SHASCHED = 8 };
+enum { OP_LIN = 1, OP_MUL = 2, OP_BITS = 3, OP_INV = 4, OP_ASSERT = 5, OP_BITSLC = 6, OP_SHAROUND = 7, OP_SHASCHED = 8, OP_QUINSEL = 9 };
 constexpr uint32_t NZ_INV_TAB = 1024;
 constexpr uint32_t NZ_LONG_LC = 24;  // an LC (or bit decomposition) longer than this is evaluated by a whole warp
 
@@ -297,6 +297,39 @@ __device__ __noinline__ void sha_step_warp(const ProgView& pv, Fr* __restrict__ 
     }
 }
 
+// ---- QuinSelector(N) as one instruction (builder.OP_QUINSEL; circuits/quinSelector.circom:26-41, the GetV of
+// cbortpl.circom:79-90 and every selector of the CBOR walk).  For each choice i the circuit has three signals:
+// eqs[i].inv (IsZero's hint: 1/(i - index) or 0), eqs[i].out (i == index) and sums[i] (the running sum, which is
+// in[index] from i = index on and 0 before).  One warp writes all 3 N of them from the index and ONE input value.
+template <uint32_t TAG>
+__device__ __noinline__ void quinsel_warp(const ProgView& pv, Fr* __restrict__ W, uint32_t p, uint32_t lane) {
+    const uint32_t N = pv.code[p + 1], w0 = pv.code[p + 2], refs = p + 3;
+    const GlobalCode gc{pv.code};
+    uint32_t q = refs + N;
+    const Fr index = eval_lc(pv, gc, W, q);  // every lane: same addresses, one transaction
+    const bool valid = fits_u32(index) && index.v[0] < N;
+    Fr val = Fr::zero();
+    if (valid) {
+        const uint32_t ref = pv.code[refs + index.v[0]];
+        if (!(ref & 0x80000000u)) {
+            val = W[ref];
+        } else {
+            uint32_t r = p + (ref & 0x7fffffffu);
+            val = eval_lc(pv, gc, W, r);
+        }
+    }
+    for (uint32_t i = lane; i < N; i += 32) {
+        Fr d = Fr::zero();
+        d.v[0] = i;
+        d = d - index;
+        Fr eq = Fr::zero();
+        eq.v[0] = d.is_zero() ? 1u : 0u;
+        W[w0 + 3 * i] = inv_or_zero(pv, d);
+        W[w0 + 3 * i + 1] = eq;
+        W[w0 + 3 * i + 2] = (valid && i >= index.v[0]) ? val : Fr::zero();
+    }
+}
+
 // Executes the instruction whose words rd() serves from offset p.  WARP: all 32 lanes cooperate on its LCs (lane 0
 // commits; code stream only); else one thread.
 template <bool WARP, class RD, uint32_t TAG = 0>
@@ -335,7 +368,9 @@ __device__ __forceinline__ bool exec_instr(const ProgView& pv, const RD& rd, Fr*
         }
     } else if (op == OP_INV) {
         if (commit) W[rd(p + 1)] = inv_or_zero(pv, W[rd(p + 2)]);
-    } else if (op == OP_SHAROUND || op == OP_SHASCHED) {  // always scheduled as a one-warp instruction (loader)
+    } else if (op == OP_QUINSEL) {  // always scheduled as a one-warp instruction (loader)
+        if (WARP) quinsel_warp<TAG>(pv, W, p, lane);
+    } else if (op == OP_SHAROUND || op == OP_SHASCHED) {
         if (WARP) {
             if (pv.code[p + 1] == 64) sha_step_warp<uint64_t, TAG>(pv, W, p, lane, op);
             else sha_step_warp<uint32_t, TAG>(pv, W, p, lane, op);
@@ -575,6 +610,24 @@ extern "C" int32_t nzcb_circuit_load(nzcb_ctx* ctx, const uint8_t* data, size_t 
                 ok = p + 3 <= c->n_code && code[p + 1] < c->n_total && code[p + 2] < c->n_total;
             } else if (op == OP_ASSERT) {
                 p += 1; ok = lc_ok(p) && lc_ok(p) && lc_ok(p);
+            } else if (op == OP_QUINSEL) {
+                ok = (uint64_t)p + 3 <= c->n_code;
+                const uint32_t N = ok ? code[p + 1] : 0, w0 = ok ? code[p + 2] : 0;
+                ok = ok && N >= 1 && N <= (1u << 20) && (uint64_t)w0 + 3ull * N <= c->n_total && (uint64_t)p + 3 + N <= c->n_code;
+                if (ok) {
+                    uint32_t q = p + 3 + N;
+                    ok = lc_ok(q);
+                    for (uint32_t k = 0; ok && k < N; k++) {
+                        const uint32_t ref = code[p + 3 + k];
+                        if (ref & 0x80000000u) {
+                            uint32_t r = p + (ref & 0x7fffffffu);
+                            ok = r >= p + 3 + N && lc_ok(r);
+                        } else {
+                            ok = ref < c->n_total;
+                        }
+                    }
+                }
+                cur_weight = 1u << 20;  // one warp, first in its level
             } else if (op == OP_SHAROUND || op == OP_SHASCHED) {
                 const uint32_t hdr = op == OP_SHAROUND ? 12u : 10u, nw = op == OP_SHAROUND ? 9u : 4u;
                 ok = (uint64_t)p + hdr <= c->n_code;
@@ -623,7 +676,7 @@ extern "C" int32_t nzcb_circuit_load(nzcb_ctx* ctx, const uint8_t* data, size_t 
             const uint32_t p = ioff_sorted[k];
             const uint32_t op = code[p];
             uint32_t len;
-            if (op == OP_SHAROUND || op == OP_SHASCHED) len = REC_WORDS + 1;  // never a record: runs from the code stream
+            if (op == OP_SHAROUND || op == OP_SHASCHED || op == OP_QUINSEL) len = REC_WORDS + 1;  // never a record: code stream
             else if (op == OP_BITS) len = 4;
             else if (op == OP_INV) len = 3;
             else if (op == OP_BITSLC) len = 3 + 2 + 2 * code[p + 3];

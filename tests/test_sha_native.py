@@ -149,3 +149,74 @@ def test_gpu_native_program_equals_the_generic_witness(ctx):
             assert rc == 0
             assert raw[k * art.n_witness * 32:(k + 1) * art.n_witness * 32] == wires[:art.n_witness * 32]
         cir.close()
+
+
+# ---- QuinSelector as one instruction (builder.OP_QUINSEL, csrc/witness.cu quinsel_warp) -----------------------------
+def _emulate_quinsel(pl, W, nw):
+    from nzcb_circom_b200.circom.builder import R as RR
+
+    def val(lc):
+        v = lc.k
+        for w, cf in lc.t.items():
+            v += cf * W[w if w >= 0 else nw + (-w - 1)]
+        return v % RR
+
+    index, N, w0 = val(pl["index"]), len(pl["ins"]), pl["w0"]
+    valid = index < N
+    picked = val(pl["ins"][index]) if valid else 0
+    out = {}
+    for i in range(N):
+        d = (i - index) % RR
+        out[w0 + 3 * i] = pow(d, RR - 2, RR) if d else 0
+        out[w0 + 3 * i + 1] = 1 if d == 0 else 0
+        out[w0 + 3 * i + 2] = picked if valid and i >= index else 0
+    return out
+
+
+def test_native_quinselector_reproduces_the_generic_witness():
+    from nzcb_circom_b200.circom.builder import OP_QUINSEL
+    from nzcb_circom_b200.circom_tester import MAINS
+
+    rng = random.Random(9)
+    for name, make in (("quinSelector5_test", lambda: {"in": [rng.randrange(R) for _ in range(5)], "index": rng.randrange(5)}),
+                       ("getV5_test", None), ("skipValue5_test", None), ("readCredSubj_exampleTest", None)):
+        c = Circuit(name)
+        MAINS[name](c)
+        art = c.finalize().artifact()
+        fused = [i[1] for i in c.prog if i[0] == OP_QUINSEL]
+        assert fused and art.n_instr_native < art.n_instr
+        prog = vm.Program(art.wprog_bytes())
+        if make is not None:
+            inputs = [make() for _ in range(6)]
+        elif name == "getV5_test":
+            inputs = [{"bytes": [9, 8, 7, 6, 5], "pos": k} for k in range(5)]
+        elif name == "skipValue5_test":
+            inputs = [{"bytes": [0x83, 23, 23, 23, 0], "pos": 0}, {"bytes": [0x62, 65, 66, 0, 0], "pos": 0}]
+        else:
+            from nzcb_circom_b200 import nzcp_helpers as H
+            cose = H.getCOSE(H.EXAMPLE_PASS_URI)
+            tbs = H.encodeToBeSigned(cose["bodyProtected"], cose["payload"])
+            inputs = [{"mapLen": 3, "bytes": list(H.fitBytes(tbs, 314)), "pos": 247}]
+        for inp in inputs:
+            W = vm.run(prog, art.flatten_input(inp), full=True)
+            for pl in fused:
+                for w, v in _emulate_quinsel(pl, W, art.n_witness).items():
+                    assert W[w] == v, (name, pl["w0"], w)
+
+
+@pytest.mark.gpu
+def test_gpu_native_quinselector_out_of_range_index_is_rejected_not_miscomputed(ctx):
+    """index >= choices: the LessThan assert rejects the pass; in range: every wire equals the C oracle's"""
+    from nzcb_circom_b200.circom_tester import wasm_tester
+    from oracle import c_oracle as C
+
+    cir = wasm_tester("quinSelector5_test", ctx)
+    art = cir.compiled
+    assert art.wprog_bytes(native=True) != art.wprog_bytes()
+    inputs = [{"in": [3, 1, 4, 1, 5], "index": k} for k in range(5)] + [{"in": [3, 1, 4, 1, 5], "index": 7}]
+    raw, st = cir.calculateWitnessBatch(inputs, True, ctx)
+    assert st == [0] * 5 + [-6]
+    for k in range(5):
+        flat = b"".join(int(v).to_bytes(32, "little") for v in art.flatten_input(inputs[k]))
+        rc, wires = C.witness(art.wprog_bytes(), flat, art.n_total)
+        assert rc == 0 and raw[k * art.n_witness * 32:(k + 1) * art.n_witness * 32] == wires[:art.n_witness * 32]
