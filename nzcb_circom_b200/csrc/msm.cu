@@ -119,7 +119,10 @@ __device__ __forceinline__ bool above_half(const Fr& s) {
 // Signed-digit recode of one scalar per thread; the digit loop is warp uniform so that lanes holding the SAME bucket
 // key (wire values are mostly 0 / +-1 / bytes in round 1) combine their atomics: one atomicAdd per distinct key
 // and warp, the lanes of a group take consecutive slots.
-template <bool COUNT>
+// AGG: warp-aggregated atomics (__match_any_sync) -- pays when many lanes hit the same bucket (wire values in the
+// Lagrange basis); with uniform scalars and 2^19 buckets two lanes of a warp almost never meet, and the match
+// instruction itself was most of the kernel's stall time (ncu: short_scoreboard 21, mio_throttle 12 per issue).
+template <bool COUNT, bool AGG>
 __global__ void __launch_bounds__(256) k_msm_digits(DigitArgs a, uint32_t* __restrict__ cnt,
                                                     const uint32_t* __restrict__ offsets, uint32_t* __restrict__ sorted) {
     const uint32_t k = blockIdx.y;
@@ -157,13 +160,17 @@ __global__ void __launch_bounds__(256) k_msm_digits(DigitArgs a, uint32_t* __res
         if (!has) continue;  // the lanes with a digit stay converged on `active`
         const uint32_t set = a.unified ? k : k * a.W + w;
         const uint32_t key = set * a.nbw + (d - 1);
-        const uint32_t peers = __match_any_sync(active, key);
-        const uint32_t leader = __ffs(peers) - 1;
-        const uint32_t rank = __popc(peers & ((1u << lane) - 1));
-        uint32_t base = 0;
-        if (lane == leader) base = atomicAdd(&cnt[key], (uint32_t)__popc(peers));
+        uint32_t base = 0, rank = 0;
+        if (AGG) {
+            const uint32_t peers = __match_any_sync(active, key);
+            const uint32_t leader = __ffs(peers) - 1;
+            rank = __popc(peers & ((1u << lane) - 1));
+            if (lane == leader) base = atomicAdd(&cnt[key], (uint32_t)__popc(peers));
+            if (!COUNT) base = __shfl_sync(peers, base, leader);
+        } else {
+            base = atomicAdd(&cnt[key], 1u);
+        }
         if (!COUNT) {
-            base = __shfl_sync(peers, base, leader);
             const uint32_t ref = a.unified ? w * a.stride + i : i;
             sorted[offsets[key] + base + rank] = ref | ((neg != dneg) ? 0x80000000u : 0u);
         }
@@ -507,6 +514,36 @@ __global__ void __launch_bounds__(128) k_bred_pair(const G1XYZZ* __restrict__ X,
     }
 }
 
+// The last levels of the same recursion in ONE launch: one CTA per bucket set walks the remaining `bits` halvings
+// with a barrier between levels instead of a launch (a level is one point addition deep: ~10 us of dependent
+// multiplies against ~70 us per launch of a nearly empty grid).  The two roles of k_bred_pair share the CTA.
+constexpr uint32_t BRED_TAIL_BITS = 9, BRED_TAIL_THREADS = 512;
+__global__ void __launch_bounds__(BRED_TAIL_THREADS) k_bred_tail(G1XYZZ* Xa, G1XYZZ* Pa, G1XYZZ* Xb, G1XYZZ* Pb, uint32_t bits,
+                                                                G1XYZZ* __restrict__ out) {
+    const size_t base = (size_t)blockIdx.x << bits;
+    Xa += base; Pa += base; Xb += base; Pb += base;
+    for (uint32_t b = bits; b > 0; b--) {
+        const uint32_t pairs = 1u << (b - 1);
+        for (uint32_t i = threadIdx.x; i < 2 * pairs; i += blockDim.x) {
+            if (i < pairs) {
+                G1XYZZ r = Xa[2 * i];
+                r.add(Xa[2 * i + 1]);
+                Xb[i] = r.dbl();
+            } else {
+                const uint32_t j = i - pairs;
+                G1XYZZ q = Pa[2 * j];
+                q.add(Pa[2 * j + 1]);
+                q.add(Xa[2 * j + 1]);
+                Pb[j] = q;
+            }
+        }
+        __syncthreads();
+        G1XYZZ* t = Xa; Xa = Xb; Xb = t;
+        t = Pa; Pa = Pb; Pb = t;
+    }
+    if (threadIdx.x == 0) out[blockIdx.x] = Pa[0];
+}
+
 // window mode: job k's result = sum_w 2^(c w) * set[k*W + w]   (Horner, one thread per job)
 __global__ void k_msm_horner(const G1XYZZ* __restrict__ sets, uint32_t W, uint32_t c, G1XYZZ* __restrict__ out) {
     const uint32_t k = blockIdx.x;
@@ -620,14 +657,18 @@ static int msm_run(nzcb_ctx* ctx, const G1Affine* d_bases, const MsmPlan& p, con
     // 1-3: sort the point references by bucket
     NZ_CUDA(ctx, cudaMemsetAsync(counts, 0, (n_keys + 1) * 4, ctx->stream));
     const dim3 dgrid(div_up(n_max, 256), (unsigned)K);
-    NZ_LAUNCH(ctx, k_msm_digits<true>, dgrid, 256, 0, da, counts, nullptr, nullptr);
+    // aggregate the atomics of a warp when buckets are few or the scalars are known to be wire-like
+    const bool agg = p.sparse || n_keys < ((size_t)1 << 16);
+    if (agg) NZ_LAUNCH(ctx, (k_msm_digits<true, true>), dgrid, 256, 0, da, counts, nullptr, nullptr);
+    else NZ_LAUNCH(ctx, (k_msm_digits<true, false>), dgrid, 256, 0, da, counts, nullptr, nullptr);
     if (R) {
         NZ_LAUNCH(ctx, k_pad_counts, div_up(n_keys, 256), 256, 0, counts, n_keys, R);
         NZ_CUDA(ctx, cudaMemsetAsync(sorted, 0xff, e_max * 4, ctx->stream));  // AFF_NULL in the padding slots
     }
     NZ_TRY(scan_excl(ctx, counts, offsets, n_keys));
     NZ_CUDA(ctx, cudaMemsetAsync(counts, 0, (n_keys + 1) * 4, ctx->stream));
-    NZ_LAUNCH(ctx, k_msm_digits<false>, dgrid, 256, 0, da, counts, offsets, sorted);
+    if (agg) NZ_LAUNCH(ctx, (k_msm_digits<false, true>), dgrid, 256, 0, da, counts, offsets, sorted);
+    else NZ_LAUNCH(ctx, (k_msm_digits<false, false>), dgrid, 256, 0, da, counts, offsets, sorted);
     NZ_CUDA(ctx, cudaMemsetAsync(buckets, 0, n_keys * sizeof(G1XYZZ), ctx->stream));  // ZZ = 0: infinity
     NZ_CUDA(ctx, cudaMemsetAsync(pk0, 0xff, (size_t)2 * T1 * 4, ctx->stream));            // KEY_NONE beyond the last chunk
     NZ_CUDA(ctx, cudaMemsetAsync(tile_counter, 0, 4, ctx->stream));
@@ -697,7 +738,16 @@ static int msm_run(nzcb_ctx* ctx, const G1Affine* d_bases, const MsmPlan& p, con
     G1XYZZ *xo = rx0, *po = rp0, *xo2 = rx1, *po2 = rp1;
     uint32_t bits = p.c - 1;  // log2 of the per-set length
     int one_based = 1;
+    G1XYZZ* tail_out = nullptr;  // set when k_bred_tail produced the per-set results
     while (bits > 0) {
+        if (!one_based && bits <= BRED_TAIL_BITS) {  // the remaining levels in one launch, one CTA per set
+            tail_out = (G1XYZZ*)ctx->scratch_get("msm_tail_out", (size_t)p.G * sizeof(G1XYZZ));
+            if (!tail_out) return ctx->fail(NZCB_E_NOMEM, "msm: out of device memory");
+            NZ_LAUNCH(ctx, k_bred_tail, p.G, BRED_TAIL_THREADS, 0, const_cast<G1XYZZ*>(X), const_cast<G1XYZZ*>(P), xo, po, bits, tail_out);
+            P = tail_out;
+            bits = 0;
+            break;
+        }
         if (one_based) {  // first level: every bucket, throughput bound -- serial running sums over chunks of 8
             const uint32_t log_S = bits >= 3 ? 3 : bits;
             bits -= log_S;

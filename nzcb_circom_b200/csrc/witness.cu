@@ -476,7 +476,7 @@ __global__ void __launch_bounds__(T, CTAS_PER_SM) k_witness(ProgView pv, const F
             }
             if (hi + nl_n + threadIdx.x < hi_n) prefetch(buf ^ 1, hi + nl_n + threadIdx.x);
             __pipeline_commit();
-            for (uint32_t i = lo + warp; i < lo + nl; i += n_warps) failed |= exec_instr<true, GlobalCode, T>(pv, gcode, W, pv.ioff[i], lane);
+            for (uint32_t i = lo + warp; i < lo + nl; i += n_warps) failed |= exec_instr<true, GlobalCode, T * 16 + CTAS_PER_SM>(pv, gcode, W, pv.ioff[i], lane);
             uint32_t i = lo + nl + threadIdx.x;
             if (i < hi) {
                 __pipeline_wait_prior(1);  // everything but the copy just issued has landed: this level's record
@@ -728,17 +728,26 @@ int witness_dev(nzcb_ctx* ctx, const nzcb_circuit* c, const Fr* d_inputs, size_t
     NZ_CUDA(ctx, cudaMemsetAsync(d_status, 0, B * sizeof(int32_t), ctx->stream));
     constexpr size_t smem = (size_t)2 * 8 * WIT_THREADS * sizeof(uint4);
     constexpr size_t smem_b = (size_t)2 * 8 * WIT_THREADS_BATCH * sizeof(uint4);
+    constexpr size_t smem_64 = (size_t)2 * 8 * 64 * sizeof(uint4);
     static const bool attr_set = [] {
         return cudaFuncSetAttribute(k_witness<WIT_THREADS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess &&
-               cudaFuncSetAttribute(k_witness<WIT_THREADS_BATCH, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b) == cudaSuccess;
+               cudaFuncSetAttribute(k_witness<WIT_THREADS_BATCH, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b) == cudaSuccess &&
+               cudaFuncSetAttribute(k_witness<WIT_THREADS_BATCH, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b) == cudaSuccess &&
+               cudaFuncSetAttribute(k_witness<64, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_64) == cudaSuccess;
     }();
     if (!attr_set) return ctx->fail(NZCB_E_CUDA, "witness: cannot reserve %zu bytes of shared memory", smem);
     static const int force = [] {
-        const char* e = getenv("NZCB_WITNESS_CTA");  // 384 / 128: pin one variant (measurements)
+        const char* e = getenv("NZCB_WITNESS_CTA");  // 384 / 128 / 1284 (128 threads, 4 per SM) / 64: pin one variant (measurements)
         return e ? atoi(e) : 0;
     }();
     const bool batch = force ? force != (int)WIT_THREADS : B > (size_t)ctx->sm_count;
-    if (batch) {
+    if (batch && force == 64) {
+        const uint32_t grid = (uint32_t)std::min<size_t>(B, (size_t)ctx->sm_count * 6);
+        NZ_LAUNCH(ctx, (k_witness<64, 6>), grid, 64, smem_64, pv, d_inputs, d_wires, d_status, (uint32_t)B);
+    } else if (batch && force == 1284) {
+        const uint32_t grid = (uint32_t)std::min<size_t>(B, (size_t)ctx->sm_count * 4);
+        NZ_LAUNCH(ctx, (k_witness<WIT_THREADS_BATCH, 4>), grid, WIT_THREADS_BATCH, smem_b, pv, d_inputs, d_wires, d_status, (uint32_t)B);
+    } else if (batch) {
         const uint32_t grid = (uint32_t)std::min<size_t>(B, (size_t)ctx->sm_count * 3);
         NZ_LAUNCH(ctx, (k_witness<WIT_THREADS_BATCH, 3>), grid, WIT_THREADS_BATCH, smem_b, pv, d_inputs, d_wires, d_status, (uint32_t)B);
     } else {
