@@ -208,6 +208,11 @@ int32_t nzcb_vkey_to_json(const uint8_t* zkey, size_t zkey_len, char* buf, size_
 int32_t nzcb_witness_batch_ex(nzcb_ctx* ctx, const nzcb_circuit* c, const uint8_t* inputs_le, size_t B,
                               uint8_t* outputs_le, uint64_t* digest, size_t sample_stride, uint8_t* wtns_sample_out,
                               int32_t* status);
+/* the same with the marshalled inputs already resident in HBM (nzcb_dev_alloc / nzcb_pass_ingest_batch_dev): the
+ * device-resident witness throughput of bench.py's roofline_witness */
+int32_t nzcb_witness_batch_ex_dev(nzcb_ctx* ctx, const nzcb_circuit* c, const void* d_inputs_le, size_t B,
+                                  uint8_t* outputs_le, uint64_t* digest, size_t sample_stride, uint8_t* wtns_sample_out,
+                                  int32_t* status);
 
 /* snarkjs plonk.fullProve for B passes: witness program then prover, wires never leave HBM.
  * status[i] = 0, NZCB_E_ASSERT (pass rejected by the circuit) or a prover error; a failed

@@ -78,6 +78,7 @@ SIGNATURES = {
     "nzcb_wtns_export": (_i32, [_vp, _u32, _vp, ctypes.POINTER(_sz)]),
     "nzcb_vkey_to_json": (_i32, [_vp, _sz, _vp, ctypes.POINTER(_sz)]),
     "nzcb_witness_batch_ex": (_i32, [_vp, _vp, _vp, _sz, _vp, _vp, _sz, _vp, _vp]),
+    "nzcb_witness_batch_ex_dev": (_i32, [_vp, _vp, _vp, _sz, _vp, _vp, _sz, _vp, _vp]),
     "nzcb_plonk_fullprove_batch": (_i32, [_vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp]),
     "nzcb_plonk_fullprove_batch_dev": (_i32, [_vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp]),
     "nzcb_vkey_from_zkey": (_i32, [_vp, _vp, _sz, ctypes.POINTER(_vp)]),

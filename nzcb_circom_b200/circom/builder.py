@@ -447,7 +447,7 @@ class Compiled:
                 pl["index"] = rlc(pl["index"])
                 pl["ins"] = [rlc(b) for b in pl["ins"]]
                 l = 1 + max((level[w] for b in pl["ins"] + [pl["index"]] for w in b.t), default=0)
-                for w in range(pl["w0"], pl["w0"] + 3 * len(pl["ins"])):
+                for w in pl["eq_w"] + [x - 1 for x in pl["eq_w"]] + [x for x in pl["sum_w"] if x is not None]:
                     level[w] = l
                 prog.append((op, pl))
             elif op == OP_LIN:
@@ -535,8 +535,8 @@ class Compiled:
                      (bits of a b c d e f g h w, LSB first)        -- native program only
            SHASCHED op, n, r1a r1b r1c (sigma1, r1c a shift), r0a r0b r0c (sigma0), w0, size, 4 n x <bit>, <lc>...
                      (bits of w[t-2], w[t-7], w[t-15], w[t-16])    -- native program only
-           QUINSEL  op, N, w0, N x <bit> (the inputs), <lc index>, <lc>...  -- native program only; writes
-                     inv_i, eq_i, sum_i at w0 + 3 i
+           QUINSEL  op, N, N x (eq wire, sum wire | 0xffffffff), N x <bit> (the inputs), <lc index>, <lc>...
+                     -- native program only; the IsZero inverse of choice i is the wire before its eq wire
            <bit> = wire id, or 0x80000000 | offset (from the instruction's first word) of the <lc> giving the value
            <lc> = n_terms, const_idx (0xffffffff = no constant), then n_terms x (wire, coef_idx)"""
         consts = {1: 0, R - 1: 1}
@@ -566,7 +566,9 @@ class Compiled:
             if op == OP_QUINSEL:
                 pl = ins[1]
                 start = ioff[-1]
-                code.extend((len(pl["ins"]), pl["w0"]))
+                code.append(len(pl["ins"]))
+                for ew, sw in zip(pl["eq_w"], pl["sum_w"]):
+                    code.extend((ew, 0xFFFFFFFF if sw is None else sw))
                 refs = len(code)
                 code.extend([0] * len(pl["ins"]))
                 emit_lc(pl["index"])

@@ -26,18 +26,28 @@ def quin_selector(c: Circuit, ins, index):
         c.assert_eq(lt, 1)
     p0, w0 = len(c.prog), c.n_wires
     chain = c.chain()                                     # sums[i] <== eqs[i] * in[i] + sums[i-1]
-    eqs = []
+    eqs, sums = [], []
     for i in range(choices):
         eq = is_zero(c, i - index)                        # :32-33
         eqs.append(eq)
-        chain.step(eq, ins[i])                            # :37
-    sums = [w for w, _, _ in chain.steps]
+        sums.append(chain.step(eq, ins[i]))               # :37
     out = chain.finish()                                  # :41  (0 when choices == 0)
-    # regular layout (no constant folding): inv_i, eq_i, sum_i at w0 + 3 i -- then the whole selector is also one
-    # word-level instruction of the native witness program
-    if choices > 0 and c.n_wires - w0 == 3 * choices and len(sums) == choices and \
-            all(eqs[i].single_wire() == w0 + 3 * i + 1 and sums[i] == w0 + 3 * i + 2 for i in range(choices)):
-        c.fuse(p0, OP_QUINSEL, {"w0": w0, "index": index, "ins": [LC.of(x) for x in ins]})
+    # The whole selector is also ONE word-level instruction of the native witness program: per choice the IsZero
+    # inverse, the equality flag and -- where the input is not a constant, so that the running sum is a signal --
+    # the sum.  Only when every signal allocated above is one of those (a signal index, nothing folded away).
+    if choices > 0 and not index.is_const():
+        eq_w = [e.single_wire() for e in eqs]
+        sum_w, seen = [], set()
+        for sacc in sums:
+            w = sacc.single_wire()
+            fresh = w is not None and w >= w0 and w not in seen
+            if fresh:
+                seen.add(w)
+            sum_w.append(w if fresh else None)
+        if all(w is not None and w > w0 for w in eq_w) and \
+                c.n_wires - w0 == 2 * choices + sum(1 for w in sum_w if w is not None) and \
+                len(set(eq_w) | {w - 1 for w in eq_w} | seen) == c.n_wires - w0:
+            c.fuse(p0, OP_QUINSEL, {"w0": w0, "index": index, "ins": [LC.of(x) for x in ins], "eq_w": eq_w, "sum_w": sum_w})
     return out
 
 

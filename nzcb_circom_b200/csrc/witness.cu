@@ -303,7 +303,7 @@ __device__ __noinline__ void sha_step_warp(const ProgView& pv, Fr* __restrict__ 
 // in[index] from i = index on and 0 before).  One warp writes all 3 N of them from the index and ONE input value.
 template <uint32_t TAG>
 __device__ __noinline__ void quinsel_warp(const ProgView& pv, Fr* __restrict__ W, uint32_t p, uint32_t lane) {
-    const uint32_t N = pv.code[p + 1], w0 = pv.code[p + 2], refs = p + 3;
+    const uint32_t N = pv.code[p + 1], dsts = p + 2, refs = dsts + 2 * N;
     const GlobalCode gc{pv.code};
     uint32_t q = refs + N;
     const Fr index = eval_lc(pv, gc, W, q);  // every lane: same addresses, one transaction
@@ -319,14 +319,15 @@ __device__ __noinline__ void quinsel_warp(const ProgView& pv, Fr* __restrict__ W
         }
     }
     for (uint32_t i = lane; i < N; i += 32) {
+        const uint32_t eq_w = pv.code[dsts + 2 * i], sum_w = pv.code[dsts + 2 * i + 1];
         Fr d = Fr::zero();
         d.v[0] = i;
         d = d - index;
         Fr eq = Fr::zero();
         eq.v[0] = d.is_zero() ? 1u : 0u;
-        W[w0 + 3 * i] = inv_or_zero(pv, d);
-        W[w0 + 3 * i + 1] = eq;
-        W[w0 + 3 * i + 2] = (valid && i >= index.v[0]) ? val : Fr::zero();
+        W[eq_w - 1] = inv_or_zero(pv, d);
+        W[eq_w] = eq;
+        if (sum_w != 0xffffffffu) W[sum_w] = (valid && i >= index.v[0]) ? val : Fr::zero();
     }
 }
 
@@ -611,17 +612,22 @@ extern "C" int32_t nzcb_circuit_load(nzcb_ctx* ctx, const uint8_t* data, size_t 
             } else if (op == OP_ASSERT) {
                 p += 1; ok = lc_ok(p) && lc_ok(p) && lc_ok(p);
             } else if (op == OP_QUINSEL) {
-                ok = (uint64_t)p + 3 <= c->n_code;
-                const uint32_t N = ok ? code[p + 1] : 0, w0 = ok ? code[p + 2] : 0;
-                ok = ok && N >= 1 && N <= (1u << 20) && (uint64_t)w0 + 3ull * N <= c->n_total && (uint64_t)p + 3 + N <= c->n_code;
+                ok = (uint64_t)p + 2 <= c->n_code;
+                const uint32_t N = ok ? code[p + 1] : 0;
+                ok = ok && N >= 1 && N <= (1u << 20) && (uint64_t)p + 2 + 3ull * N <= c->n_code;
                 if (ok) {
-                    uint32_t q = p + 3 + N;
-                    ok = lc_ok(q);
+                    const uint32_t dsts = p + 2, refs = dsts + 2 * N;
                     for (uint32_t k = 0; ok && k < N; k++) {
-                        const uint32_t ref = code[p + 3 + k];
+                        const uint32_t ew = code[dsts + 2 * k], sw = code[dsts + 2 * k + 1];
+                        ok = ew >= 1 && ew < c->n_total && (sw == 0xffffffffu || sw < c->n_total);
+                    }
+                    uint32_t q = refs + N;
+                    ok = ok && lc_ok(q);
+                    for (uint32_t k = 0; ok && k < N; k++) {
+                        const uint32_t ref = code[refs + k];
                         if (ref & 0x80000000u) {
                             uint32_t r = p + (ref & 0x7fffffffu);
-                            ok = r >= p + 3 + N && lc_ok(r);
+                            ok = r >= refs + N && lc_ok(r);
                         } else {
                             ok = ref < c->n_total;
                         }
@@ -761,16 +767,24 @@ uint32_t circuit_n_witness(const nzcb_circuit* c) { return c->n_witness; }
 uint32_t circuit_n_in(const nzcb_circuit* c) { return c->n_in; }
 }  // namespace nzcb
 
+// passes per launch of a large batch: as many as ~24 GiB of wires hold, rounded down to whole waves of the batch kernel
+static size_t witness_chunk(const nzcb_ctx* ctx, size_t per_pass, size_t B) {
+    size_t chunk = std::max<size_t>(1, ((size_t)24 << 30) / per_pass);
+    const size_t wave = (size_t)ctx->sm_count * 3;
+    if (chunk > wave) chunk -= chunk % wave;
+    return std::min(chunk, B);
+}
+
 extern "C" int32_t nzcb_witness_batch(nzcb_ctx* ctx, const nzcb_circuit* c, const uint8_t* inputs_le, size_t B,
                                       uint8_t* wtns_out, int32_t* status) {
     if (!ctx || !c || (!inputs_le && c->n_in) || !status) return NZCB_E_INVALID;
     if (c->ctx != ctx) return ctx->fail(NZCB_E_INVALID, "circuit was loaded on a different context");
     if (B == 0) return 0;
     NZ_CUDA(ctx, cudaSetDevice(ctx->device));
-    // bound the device footprint: process the batch in chunks of at most ~8 GiB of wires
+    // bound the device footprint: process the batch in chunks of at most ~24 GiB of wires, a whole number of waves
+    // of the batch kernel (3 CTAs per SM) so that no launch leaves CTA slots empty
     const size_t per_pass = (size_t)c->n_total * sizeof(Fr);
-    size_t chunk = std::max<size_t>(1, ((size_t)8 << 30) / per_pass);
-    if (chunk > B) chunk = B;
+    const size_t chunk = witness_chunk(ctx, per_pass, B);
     Fr* d_w = (Fr*)ctx->scratch_get("wt_wires", chunk * per_pass);
     Fr* d_in = (Fr*)ctx->scratch_get("wt_inputs", std::max<size_t>(32, chunk * (size_t)c->n_in * sizeof(Fr)));
     int32_t* d_st = (int32_t*)ctx->scratch_get("wt_status", chunk * sizeof(int32_t));
@@ -831,16 +845,31 @@ __global__ void __launch_bounds__(256) k_witness_digest(const Fr* __restrict__ w
 }
 }  // namespace
 
+static int32_t witness_batch_ex_impl(nzcb_ctx* ctx, const nzcb_circuit* c, const uint8_t* inputs_le, bool inputs_on_device,
+                                     size_t B, uint8_t* outputs_le, uint64_t* digest, size_t sample_stride,
+                                     uint8_t* wtns_sample_out, int32_t* status);
+
 extern "C" int32_t nzcb_witness_batch_ex(nzcb_ctx* ctx, const nzcb_circuit* c, const uint8_t* inputs_le, size_t B,
                                          uint8_t* outputs_le, uint64_t* digest, size_t sample_stride,
                                          uint8_t* wtns_sample_out, int32_t* status) {
+    return witness_batch_ex_impl(ctx, c, inputs_le, false, B, outputs_le, digest, sample_stride, wtns_sample_out, status);
+}
+extern "C" int32_t nzcb_witness_batch_ex_dev(nzcb_ctx* ctx, const nzcb_circuit* c, const void* d_inputs_le, size_t B,
+                                             uint8_t* outputs_le, uint64_t* digest, size_t sample_stride,
+                                             uint8_t* wtns_sample_out, int32_t* status) {
+    return witness_batch_ex_impl(ctx, c, (const uint8_t*)d_inputs_le, true, B, outputs_le, digest, sample_stride,
+                                 wtns_sample_out, status);
+}
+
+static int32_t witness_batch_ex_impl(nzcb_ctx* ctx, const nzcb_circuit* c, const uint8_t* inputs_le, bool inputs_on_device,
+                                     size_t B, uint8_t* outputs_le, uint64_t* digest, size_t sample_stride,
+                                     uint8_t* wtns_sample_out, int32_t* status) {
     if (!ctx || !c || (!inputs_le && c->n_in) || !status || (wtns_sample_out && sample_stride == 0)) return NZCB_E_INVALID;
     if (c->ctx != ctx) return ctx->fail(NZCB_E_INVALID, "circuit was loaded on a different context");
     if (B == 0) return 0;
     NZ_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t per_pass = (size_t)c->n_total * sizeof(Fr);
-    size_t chunk = std::max<size_t>(1, ((size_t)8 << 30) / per_pass);
-    if (chunk > B) chunk = B;
+    const size_t chunk = witness_chunk(ctx, per_pass, B);
     Fr* d_w = (Fr*)ctx->scratch_get("wt_wires", chunk * per_pass);
     Fr* d_in = (Fr*)ctx->scratch_get("wt_inputs", std::max<size_t>(32, chunk * (size_t)c->n_in * sizeof(Fr)));
     int32_t* d_st = (int32_t*)ctx->scratch_get("wt_status", chunk * sizeof(int32_t));
@@ -849,10 +878,12 @@ extern "C" int32_t nzcb_witness_batch_ex(nzcb_ctx* ctx, const nzcb_circuit* c, c
     NZ_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     for (size_t done = 0; done < B; done += chunk) {
         const size_t nb = std::min(chunk, B - done);
-        if (c->n_in)
+        const Fr* cur_in = d_in;
+        if (inputs_on_device) cur_in = reinterpret_cast<const Fr*>(inputs_le) + done * (size_t)c->n_in;
+        else if (c->n_in)
             NZ_CUDA(ctx, cudaMemcpyAsync(d_in, inputs_le + done * (size_t)c->n_in * 32, nb * (size_t)c->n_in * 32,
                                          cudaMemcpyHostToDevice, ctx->stream));
-        NZ_TRY(witness_dev(ctx, c, d_in, nb, d_w, d_st));
+        NZ_TRY(witness_dev(ctx, c, cur_in, nb, d_w, d_st));
         NZ_CUDA(ctx, cudaMemcpyAsync(status + done, d_st, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
         if (digest) {
             NZ_LAUNCH(ctx, k_witness_digest, (unsigned)nb, 256, 0, d_w, c->n_total, c->n_witness, d_dg);

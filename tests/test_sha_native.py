@@ -161,15 +161,16 @@ def _emulate_quinsel(pl, W, nw):
             v += cf * W[w if w >= 0 else nw + (-w - 1)]
         return v % RR
 
-    index, N, w0 = val(pl["index"]), len(pl["ins"]), pl["w0"]
+    index, N = val(pl["index"]), len(pl["ins"])
     valid = index < N
     picked = val(pl["ins"][index]) if valid else 0
     out = {}
     for i in range(N):
         d = (i - index) % RR
-        out[w0 + 3 * i] = pow(d, RR - 2, RR) if d else 0
-        out[w0 + 3 * i + 1] = 1 if d == 0 else 0
-        out[w0 + 3 * i + 2] = picked if valid and i >= index else 0
+        out[pl["eq_w"][i] - 1] = pow(d, RR - 2, RR) if d else 0
+        out[pl["eq_w"][i]] = 1 if d == 0 else 0
+        if pl["sum_w"][i] is not None:
+            out[pl["sum_w"][i]] = picked if valid and i >= index else 0
     return out
 
 
@@ -179,7 +180,8 @@ def test_native_quinselector_reproduces_the_generic_witness():
 
     rng = random.Random(9)
     for name, make in (("quinSelector5_test", lambda: {"in": [rng.randrange(R) for _ in range(5)], "index": rng.randrange(5)}),
-                       ("getV5_test", None), ("skipValue5_test", None), ("readCredSubj_exampleTest", None)):
+                       ("getV5_test", None), ("skipValue5_test", None), ("readCredSubj_exampleTest", None),
+                       ("constructNullifier_test", None)):
         c = Circuit(name)
         MAINS[name](c)
         art = c.finalize().artifact()
@@ -192,6 +194,12 @@ def test_native_quinselector_reproduces_the_generic_witness():
             inputs = [{"bytes": [9, 8, 7, 6, 5], "pos": k} for k in range(5)]
         elif name == "skipValue5_test":
             inputs = [{"bytes": [0x83, 23, 23, 23, 0], "pos": 0}, {"bytes": [0x62, 65, 66, 0, 0], "pos": 0}]
+        elif name == "constructNullifier_test":   # selectors over buffers with constant (zero) tails, signal indices
+            from nzcb_circom_b200 import nzcp_helpers as H
+            inputs = [{"givenName": H.padArray(H.stringToArray(g), 64), "givenNameLen": len(g),
+                       "familyName": H.padArray(H.stringToArray(f), 64), "familyNameLen": len(f),
+                       "dob": H.padArray(H.stringToArray("1960-04-16"), 64), "dobLen": 10}
+                      for g, f in (("Jack", "Sparrow"), ("A", "B" * 21))]
         else:
             from nzcb_circom_b200 import nzcp_helpers as H
             cose = H.getCOSE(H.EXAMPLE_PASS_URI)
