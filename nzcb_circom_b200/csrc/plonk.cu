@@ -692,28 +692,32 @@ int prove_core(nzcb_ctx* ctx, const nzcb_zkey* zk, const Fr* d_w_le, const uint8
     const uint32_t n_w = zk->n_vars - zk->n_add;
     const uint32_t n = zk->n, n_pub = zk->n_public;
 
-    // blinders b1..b9 (Montgomery); index 0 unused
+    // blinders b1..b9 (Montgomery); index 0 unused.  Without injected values: one read of the OS CSPRNG for all nine
+    // (254-bit candidates, rejected above r -- probability 1/4 each -- and redrawn from the same descriptor)
     Fr bl[10];
     bl[0] = Fr::zero();
+    FILE* rnd = nullptr;
+    if (!blinders_le) {
+        rnd = fopen("/dev/urandom", "rb");
+        if (!rnd) return ctx->fail(NZCB_E_INVALID, "cannot open the OS CSPRNG");
+    }
     for (int i = 1; i <= 9; i++) {
         Fr v;
         if (blinders_le) {
             v = fr_from_le(blinders_le + (i - 1) * 32);
             if (!fr_is_canonical(v)) return ctx->fail(NZCB_E_INVALID, "blinder b%d is not a canonical Fr element", i);
         } else {
-            FILE* f = fopen("/dev/urandom", "rb");
-            if (!f) return ctx->fail(NZCB_E_INVALID, "cannot open the OS CSPRNG");
             do {
-                if (fread(v.v, 1, 32, f) != 32) {
-                    fclose(f);
+                if (fread(v.v, 1, 32, rnd) != 32) {
+                    fclose(rnd);
                     return ctx->fail(NZCB_E_INVALID, "cannot read the OS CSPRNG");
                 }
                 v.v[7] &= 0x3fffffffu;
             } while (!fr_is_canonical(v));
-            fclose(f);
         }
         bl[i] = v.to_mont();
     }
+    if (rnd) fclose(rnd);
 
     Bufs b;
     NZ_TRY(get_bufs(ctx, zk, b));
