@@ -30,7 +30,10 @@ OP_SHAROUND, OP_SHASCHED = 7, 8
 # QuinSelector(N) (circuits/quinSelector.circom:26-41) as one instruction: the N IsZero inverses, the N equality flags
 # and the N running sums written from the index and the one selected input
 OP_QUINSEL = 9
-FAT_OPS = (OP_SHAROUND, OP_SHASCHED, OP_QUINSEL)
+# a whole SHA-256 compression from round r_start on (message schedule included): the state stays in registers across
+# the rounds, one level instead of one per round.  Stands for the OP_SHASCHED / OP_SHAROUND steps it is made of.
+OP_SHABLOCK = 10
+FAT_OPS = (OP_SHAROUND, OP_SHASCHED, OP_QUINSEL, OP_SHABLOCK)
 
 
 class LC:
@@ -246,6 +249,22 @@ class Circuit:
         self.constraints.append(({}, {}, _terms(x - LC({w: 1}))))
         return LC({w: 1})
 
+    def wire_as(self, x, prog_lc):
+        """signal s; s <== x, exactly like wire(x) for the R1CS and the numbering -- but the witness PROGRAM computes
+        s from prog_lc, a linear combination of equal value with a shorter dependency chain (e.g. a prefix sum
+        spelled out instead of the previous element of a running difference)."""
+        x = LC.of(x)
+        w = self._new_wire()
+        self.prog.append((OP_LIN, w, LC.of(prog_lc)))
+        self.constraints.append(({}, {}, _terms(x - LC({w: 1}))))
+        return LC({w: 1})
+
+    def temp(self, x):
+        """program temp (not a signal, no constraint) holding the value of the linear combination x"""
+        t = self._new_temp()
+        self.prog.append((OP_LIN, t, LC.of(x)))
+        return LC({t: 1})
+
     def assign_output(self, out_lc, x):
         """out <== x for a declared main output"""
         w = out_lc.single_wire()
@@ -442,6 +461,14 @@ class Compiled:
                 for w in range(pl["w0"], pl["w0"] + pl["size"]):
                     level[w] = l
                 prog.append((op, pl))
+            elif op == OP_SHABLOCK:
+                pl = dict(ins[1])
+                pl["words"] = [[rlc(b) for b in word] for word in pl["words"]]
+                l = 1 + max((level[w] for word in pl["words"] for b in word for w in b.t), default=0)
+                for w0, size in pl["regions"]:
+                    for w in range(w0, w0 + size):
+                        level[w] = l
+                prog.append((op, pl))
             elif op == OP_QUINSEL:
                 pl = dict(ins[1])
                 pl["index"] = rlc(pl["index"])
@@ -537,6 +564,9 @@ class Compiled:
                      (bits of w[t-2], w[t-7], w[t-15], w[t-16])    -- native program only
            QUINSEL  op, N, N x (eq wire, sum wire | 0xffffffff), N x <bit> (the inputs), <lc index>, <lc>...
                      -- native program only; the IsZero inverse of choice i is the wire before its eq wire
+           SHABLOCK op, n, 12 rotation counts (Sigma1, Sigma0, sigma1, sigma0), r_start, rounds, (rounds - 16) x w0 of
+                     the schedule steps, (rounds - r_start) x w0 of the rounds, (rounds - r_start) x K (low word),
+                     24 n x <bit> (state a..h at round r_start, message words 0..15), <lc>...  -- native program only
            <bit> = wire id, or 0x80000000 | offset (from the instruction's first word) of the <lc> giving the value
            <lc> = n_terms, const_idx (0xffffffff = no constant), then n_terms x (wire, coef_idx)"""
         consts = {1: 0, R - 1: 1}
@@ -563,7 +593,27 @@ class Compiled:
             ioff.append(len(code))
             op = ins[0]
             code.append(op)
-            if op == OP_QUINSEL:
+            if op == OP_SHABLOCK:
+                pl = ins[1]
+                start = ioff[-1]
+                code.append(pl["n"])
+                for key in ("rot1", "rot0", "srot1", "srot0"):
+                    code.extend(pl[key])
+                code.extend((pl["r_start"], pl["rounds"]))
+                code.extend(pl["sched_w0"])
+                code.extend(pl["round_w0"])
+                code.extend(k & 0xFFFFFFFF for k in pl["K"])
+                refs = len(code)
+                bits = [b for word in pl["words"] for b in word]
+                code.extend([0] * len(bits))
+                for k, b in enumerate(bits):
+                    w = b.single_wire()
+                    if w is not None:
+                        code[refs + k] = w
+                    else:
+                        code[refs + k] = 0x80000000 | (len(code) - start)
+                        emit_lc(b)
+            elif op == OP_QUINSEL:
                 pl = ins[1]
                 start = ioff[-1]
                 code.append(len(pl["ins"]))

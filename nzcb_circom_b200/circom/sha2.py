@@ -13,7 +13,7 @@ parts of square / cube roots of primes) and pinned by the hashlib cross-checks o
 tests/test_nzcp.py (the digests of real and synthetic passes) and tests/test_sha_native.py."""
 from math import isqrt
 
-from .builder import LC, OP_SHAROUND, OP_SHASCHED, Circuit
+from .builder import LC, OP_SHABLOCK, OP_SHAROUND, OP_SHASCHED, Circuit
 from .circomlib import is_equal, num2bits
 
 
@@ -125,6 +125,8 @@ class _Sha2:
         n = self.n
         w = list(block_words)
         r3_1, r3_0 = self.small1[2], self.small0[2]
+        p_block = len(c.prog)
+        sched_w0, round_w0, round_state = {}, {}, {}
         for t in range(16, self.rounds):
             p0, w0 = len(c.prog), c.n_wires
             s1 = self._sigma(c, w[t - 2], self.small1)
@@ -147,6 +149,7 @@ class _Sha2:
             if regular:
                 c.fuse(p0, OP_SHASCHED, {"n": n, "rot1": list(self.small1[:3]), "rot0": list(self.small0[:3]), "w0": w0,
                                          "size": size, "words": [w[t - 2], w[t - 7], w[t - 15], w[t - 16]]})
+                sched_w0[t] = (w0, size)
         a, b, cc, d, e, f, g, h = state
         for t in range(self.rounds):
             p0, w0 = len(c.prog), c.n_wires
@@ -173,6 +176,31 @@ class _Sha2:
             if regular:
                 c.fuse(p0, OP_SHAROUND, {"n": n, "rot1": list(self.big1[:3]), "rot0": list(self.big0[:3]), "K": self.K[t],
                                          "w0": w0, "size": size, "words": ins})
+                round_w0[t] = (w0, size)
+                round_state[t] = ins[:8]
+        # A 32-bit compression whose every schedule step is regular and whose rounds are regular from some round on
+        # becomes ONE instruction of the native program (state in registers across the rounds): the step instructions
+        # recorded above, from that round on, are folded into it.  (SHA-512's padded block has constant message words,
+        # so its schedule is not regular: it keeps one instruction per step.)
+        r_start = next((t for t in range(self.rounds) if all(u in round_w0 for u in range(t, self.rounds))), None)
+        if n == 32 and r_start is not None and r_start <= 16 and len(sched_w0) == self.rounds - 16:
+            keep, folded = [], []
+            for ins_ in c.prog[p_block:]:
+                if ins_[0] == OP_SHASCHED or (ins_[0] == OP_SHAROUND and ins_[1]["w0"] >= round_w0[r_start][0]):
+                    folded.append(ins_)
+                else:
+                    keep.append(ins_)
+            generic = [g_ for f_ in folded for g_ in f_[2]]
+            del c.prog[p_block:]
+            c.prog.extend(keep)
+            c.prog.append((OP_SHABLOCK, {
+                "n": n, "rot1": list(self.big1[:3]), "rot0": list(self.big0[:3]), "srot1": list(self.small1[:3]),
+                "srot0": list(self.small0[:3]), "r_start": r_start, "rounds": self.rounds,
+                "sched_w0": [sched_w0[t][0] for t in range(16, self.rounds)],
+                "round_w0": [round_w0[t][0] for t in range(r_start, self.rounds)],
+                "K": [self.K[t] for t in range(r_start, self.rounds)],
+                "regions": [sched_w0[t] for t in range(16, self.rounds)] + [round_w0[t] for t in range(r_start, self.rounds)],
+                "words": list(round_state[r_start]) + list(block_words)}, generic))
         new = [a, b, cc, d, e, f, g, h]
         return [_binsum(c, n, [state[i], new[i]]) for i in range(8)]
 
@@ -218,9 +246,18 @@ def sha256_var(c: Circuit, in_bits, length_bits, block_space):
     msg = []
     lt = LC(None, 1)
     L_w = c.wire(L)
+    # lt_k <== lt_(k-1) - eq_k is a chain of nbytes dependent signals.  The R1CS keeps that form; the witness
+    # program computes lt_k = 1 - (eq's of the earlier blocks of BLK bytes) - (eq's of this block up to k): three
+    # levels whatever the length (the chain was hidden behind the hash rounds until those became one instruction)
+    BLK = 23
+    prefix, block_eqs = LC(), LC()
     for k in range(nbytes):
         eq = is_equal(c, k, L_w)
-        lt = c.wire(lt - eq)
+        if k % BLK == 0 and k:
+            prefix = c.temp(prefix + block_eqs) if not (prefix + block_eqs).is_const() else prefix + block_eqs
+            block_eqs = LC()
+        block_eqs = block_eqs + eq
+        lt = c.wire_as(lt - eq, 1 - prefix - block_eqs)
         for bpos in range(8):
             m = c.mul(in_bits[8 * k + bpos], lt)
             if bpos == 0:

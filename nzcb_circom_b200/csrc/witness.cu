@@ -22,7 +22,7 @@
 
 using namespace nzcb;
 
-enum { OP_LIN = 1, OP_MUL = 2, OP_BITS = 3, OP_INV = 4, OP_ASSERT = 5, OP_BITSLC = 6, OP_SHAROUND = 7, OP_SHASCHED = 8, OP_QUINSEL = 9 };
+enum { OP_LIN = 1, OP_MUL = 2, OP_BITS = 3, OP_INV = 4, OP_ASSERT = 5, OP_BITSLC = 6, OP_SHAROUND = 7, OP_SHASCHED = 8, OP_QUINSEL = 9, OP_SHABLOCK = 10 };
 constexpr uint32_t NZ_INV_TAB = 1024;
 constexpr uint32_t NZ_LONG_LC = 24;  // an LC (or bit decomposition) longer than this is evaluated by a whole warp
 
@@ -249,51 +249,104 @@ __device__ __forceinline__ void sha_put_bits(Fr* __restrict__ W, uint32_t base, 
     for (uint32_t j = lane; j < count; j += 32) sha_put(W, base + j, (uint32_t)((v >> j) & 1));
 }
 
+// one round on words: writes the round's 11 N + 6 bit wires at w0, returns the new e and a through en / an
+template <class WT>
+__device__ __forceinline__ void sha_round_emit(Fr* __restrict__ W, uint32_t w0, WT A, WT B, WT C, WT D, WT E, WT F, WT G, WT H,
+                                               WT Wt, WT K, uint32_t r1a, uint32_t r1b, uint32_t r1c, uint32_t r0a,
+                                               uint32_t r0b, uint32_t r0c, uint32_t lane, WT& e_new, WT& a_new) {
+    constexpr uint32_t N = ShaWord<WT>::N;
+    typedef typename ShaWord<WT>::Wide Wide;
+    const WT e2 = sha_rotr(E, r1b), e3 = sha_rotr(E, r1c);
+    const WT S1 = sha_rotr(E, r1a) ^ e2 ^ e3;
+    const WT ch = (E & F) ^ (~E & G);
+    const Wide t1 = (Wide)H + S1 + ch + K + Wt;
+    const WT a2 = sha_rotr(A, r0b), a3 = sha_rotr(A, r0c);
+    const WT S0 = sha_rotr(A, r0a) ^ a2 ^ a3;
+    const WT mj = (A & B) ^ (A & C) ^ (B & C);
+    const Wide t2 = (Wide)S0 + mj;
+    const Wide en = (Wide)D + (WT)t1;
+    const Wide an = (Wide)(WT)t1 + (WT)t2;
+    sha_put_xor3<WT>(W, w0, e2 & e3, S1, N, lane);
+    sha_put_bits<WT>(W, w0 + 2 * N, ch, N, lane);
+    sha_put_bits<Wide>(W, w0 + 3 * N, t1, N + 3, lane);
+    sha_put_xor3<WT>(W, w0 + 4 * N + 3, a2 & a3, S0, N, lane);
+    sha_put_xor3<WT>(W, w0 + 6 * N + 3, B & C, mj, N, lane);
+    sha_put_bits<Wide>(W, w0 + 8 * N + 3, t2, N + 1, lane);
+    sha_put_bits<Wide>(W, w0 + 9 * N + 4, en, N + 1, lane);
+    sha_put_bits<Wide>(W, w0 + 10 * N + 5, an, N + 1, lane);
+    e_new = (WT)en;
+    a_new = (WT)an;
+}
+// one message-schedule step on words: writes its 5 N + 2 - r1c - r0c bit wires at w0, returns w[t]
+template <class WT>
+__device__ __forceinline__ WT sha_sched_emit(Fr* __restrict__ W, uint32_t w0, WT x2, WT x7, WT x15, WT x16, uint32_t r1a,
+                                             uint32_t r1b, uint32_t r1c, uint32_t r0a, uint32_t r0b, uint32_t r0c,
+                                             uint32_t lane) {
+    constexpr uint32_t N = ShaWord<WT>::N;
+    typedef typename ShaWord<WT>::Wide Wide;
+    const WT b1 = sha_rotr(x2, r1b), c1 = (WT)(x2 >> r1c);
+    const WT s1 = sha_rotr(x2, r1a) ^ b1 ^ c1;
+    const WT b0 = sha_rotr(x15, r0b), c0 = (WT)(x15 >> r0c);
+    const WT s0 = sha_rotr(x15, r0a) ^ b0 ^ c0;
+    const Wide sum = (Wide)s1 + x7 + s0 + x16;
+    const uint32_t o_s0 = 2 * N - r1c, o_w = o_s0 + 2 * N - r0c;
+    sha_put_xor3<WT>(W, w0, b1 & c1, s1, N - r1c, lane);
+    sha_put_xor3<WT>(W, w0 + o_s0, b0 & c0, s0, N - r0c, lane);
+    sha_put_bits<Wide>(W, w0 + o_w, sum, N + 2, lane);
+    return (WT)sum;
+}
+
 // out of line: the interpreter's own loop is latency bound and must keep its registers.  TAG gives every kernel its
 // own copy (ptxas 12.9 segfaults when two kernels of this translation unit share an out-of-line routine).
 template <class WT, uint32_t TAG>
 __device__ __noinline__ void sha_step_warp(const ProgView& pv, Fr* __restrict__ W, uint32_t p, uint32_t lane, uint32_t op) {
-    constexpr uint32_t N = ShaWord<WT>::N;
-    typedef typename ShaWord<WT>::Wide Wide;
     const uint32_t r1a = pv.code[p + 2], r1b = pv.code[p + 3], r1c = pv.code[p + 4];
     const uint32_t r0a = pv.code[p + 5], r0b = pv.code[p + 6], r0c = pv.code[p + 7];
     if (op == OP_SHAROUND) {
         const WT K = (WT)(((uint64_t)pv.code[p + 9] << 32) | pv.code[p + 8]);
         const uint32_t w0 = pv.code[p + 10], refs = p + 12;
-        WT x[9];  // a b c d e f g h w
+        WT x[9], en, an;  // a b c d e f g h w
         sha_gather<WT, 9>(pv, W, p, refs, lane, x);
-        const WT A = x[0], B = x[1], C = x[2], D = x[3], E = x[4], F = x[5], G = x[6], H = x[7], Wt = x[8];
-        const WT e2 = sha_rotr(E, r1b), e3 = sha_rotr(E, r1c);
-        const WT S1 = sha_rotr(E, r1a) ^ e2 ^ e3;
-        const WT ch = (E & F) ^ (~E & G);
-        const Wide t1 = (Wide)H + S1 + ch + K + Wt;
-        const WT a2 = sha_rotr(A, r0b), a3 = sha_rotr(A, r0c);
-        const WT S0 = sha_rotr(A, r0a) ^ a2 ^ a3;
-        const WT mj = (A & B) ^ (A & C) ^ (B & C);
-        const Wide t2 = (Wide)S0 + mj;
-        const Wide en = (Wide)D + (WT)t1;
-        const Wide an = (Wide)(WT)t1 + (WT)t2;
-        sha_put_xor3<WT>(W, w0, e2 & e3, S1, N, lane);
-        sha_put_bits<WT>(W, w0 + 2 * N, ch, N, lane);
-        sha_put_bits<Wide>(W, w0 + 3 * N, t1, N + 3, lane);
-        sha_put_xor3<WT>(W, w0 + 4 * N + 3, a2 & a3, S0, N, lane);
-        sha_put_xor3<WT>(W, w0 + 6 * N + 3, B & C, mj, N, lane);
-        sha_put_bits<Wide>(W, w0 + 8 * N + 3, t2, N + 1, lane);
-        sha_put_bits<Wide>(W, w0 + 9 * N + 4, en, N + 1, lane);
-        sha_put_bits<Wide>(W, w0 + 10 * N + 5, an, N + 1, lane);
+        sha_round_emit<WT>(W, w0, x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7], x[8], K, r1a, r1b, r1c, r0a, r0b, r0c, lane, en, an);
     } else {
         const uint32_t w0 = pv.code[p + 8], refs = p + 10;
         WT x[4];  // w[t-2] w[t-7] w[t-15] w[t-16]
         sha_gather<WT, 4>(pv, W, p, refs, lane, x);
-        const WT b1 = sha_rotr(x[0], r1b), c1 = (WT)(x[0] >> r1c);
-        const WT s1 = sha_rotr(x[0], r1a) ^ b1 ^ c1;
-        const WT b0 = sha_rotr(x[2], r0b), c0 = (WT)(x[2] >> r0c);
-        const WT s0 = sha_rotr(x[2], r0a) ^ b0 ^ c0;
-        const Wide sum = (Wide)s1 + x[1] + s0 + x[3];
-        const uint32_t o_s0 = 2 * N - r1c, o_w = o_s0 + 2 * N - r0c;
-        sha_put_xor3<WT>(W, w0, b1 & c1, s1, N - r1c, lane);
-        sha_put_xor3<WT>(W, w0 + o_s0, b0 & c0, s0, N - r0c, lane);
-        sha_put_bits<Wide>(W, w0 + o_w, sum, N + 2, lane);
+        sha_sched_emit<WT>(W, w0, x[0], x[1], x[2], x[3], r1a, r1b, r1c, r0a, r0b, r0c, lane);
+    }
+}
+
+// A whole SHA-256 compression from round r_start on (builder.OP_SHABLOCK): the eight state words and the sixteen
+// message words are gathered once, the state lives in registers across the rounds, the 16-word schedule window is
+// spread over the lanes (lane t & 15 holds w[t]) and read with shuffles.  One warp, one level.
+template <uint32_t TAG>
+__device__ __noinline__ void sha_block_warp(const ProgView& pv, Fr* __restrict__ W, uint32_t p, uint32_t lane) {
+    const uint32_t* cd = pv.code + p;
+    const uint32_t r_start = cd[14], rounds = cd[15];
+    const uint32_t sched = p + 16, rnd = sched + (rounds - 16), kk = rnd + (rounds - r_start), refs = kk + (rounds - r_start);
+    uint32_t st[8], win = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) st[k] = __ballot_sync(0xffffffffu, sha_in_bit(pv, W, p, refs, 32, k, lane));
+    for (uint32_t k = 0; k < 16; k++) {  // message word k -> lane k of the window
+        const uint32_t v = __ballot_sync(0xffffffffu, sha_in_bit(pv, W, p, refs, 32, 8 + k, lane));
+        if (lane == k) win = v;
+    }
+    uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
+    for (uint32_t t = 16; t < r_start; t++) {}  // (r_start <= 16: the schedule starts with the rounds)
+    for (uint32_t t = r_start; t < rounds; t++) {
+        if (t >= 16) {
+            const uint32_t x2 = __shfl_sync(0xffffffffu, win, (t - 2) & 15), x7 = __shfl_sync(0xffffffffu, win, (t - 7) & 15);
+            const uint32_t x15 = __shfl_sync(0xffffffffu, win, (t - 15) & 15), x16 = __shfl_sync(0xffffffffu, win, t & 15);
+            const uint32_t wt = sha_sched_emit<uint32_t>(W, pv.code[sched + (t - 16)], x2, x7, x15, x16, cd[8], cd[9], cd[10], cd[11],
+                                                         cd[12], cd[13], lane);
+            if (lane == (t & 15)) win = wt;
+        }
+        const uint32_t wt = __shfl_sync(0xffffffffu, win, t & 15);
+        uint32_t en, an;
+        sha_round_emit<uint32_t>(W, pv.code[rnd + (t - r_start)], a, b, c, d, e, f, g, h, wt, pv.code[kk + (t - r_start)], cd[2], cd[3],
+                                 cd[4], cd[5], cd[6], cd[7], lane, en, an);
+        h = g; g = f; f = e; e = en;
+        d = c; c = b; b = a; a = an;
     }
 }
 
@@ -371,6 +424,8 @@ __device__ __forceinline__ bool exec_instr(const ProgView& pv, const RD& rd, Fr*
         if (commit) W[rd(p + 1)] = inv_or_zero(pv, W[rd(p + 2)]);
     } else if (op == OP_QUINSEL) {  // always scheduled as a one-warp instruction (loader)
         if (WARP) quinsel_warp<TAG>(pv, W, p, lane);
+    } else if (op == OP_SHABLOCK) {
+        if (WARP) sha_block_warp<TAG>(pv, W, p, lane);
     } else if (op == OP_SHAROUND || op == OP_SHASCHED) {
         if (WARP) {
             if (pv.code[p + 1] == 64) sha_step_warp<uint64_t, TAG>(pv, W, p, lane, op);
@@ -611,6 +666,29 @@ extern "C" int32_t nzcb_circuit_load(nzcb_ctx* ctx, const uint8_t* data, size_t 
                 ok = p + 3 <= c->n_code && code[p + 1] < c->n_total && code[p + 2] < c->n_total;
             } else if (op == OP_ASSERT) {
                 p += 1; ok = lc_ok(p) && lc_ok(p) && lc_ok(p);
+            } else if (op == OP_SHABLOCK) {
+                ok = (uint64_t)p + 16 <= c->n_code && code[p + 1] == 32;
+                const uint32_t r_start = ok ? code[p + 14] : 0, rounds = ok ? code[p + 15] : 0;
+                ok = ok && rounds >= 17 && rounds <= 128 && r_start <= 16;
+                if (ok) {
+                    for (uint32_t k = 2; k < 14; k++) ok = ok && code[p + k] < 32;
+                    const uint32_t sched = p + 16, rnd = sched + (rounds - 16), kk = rnd + (rounds - r_start);
+                    const uint32_t refs = kk + (rounds - r_start);
+                    ok = ok && (uint64_t)refs + 24 * 32 <= c->n_code;
+                    const uint32_t s_size = ok ? 5 * 32 + 2 - code[p + 10] - code[p + 13] : 0;
+                    for (uint32_t k = 0; ok && k < rounds - 16; k++) ok = (uint64_t)code[sched + k] + s_size <= c->n_total;
+                    for (uint32_t k = 0; ok && k < rounds - r_start; k++) ok = (uint64_t)code[rnd + k] + 11 * 32 + 6 <= c->n_total;
+                    for (uint32_t k = 0; ok && k < 24 * 32; k++) {
+                        const uint32_t ref = code[refs + k];
+                        if (ref & 0x80000000u) {
+                            uint32_t q = p + (ref & 0x7fffffffu);
+                            ok = q >= refs + 24 * 32 && lc_ok(q);
+                        } else {
+                            ok = ref < c->n_total;
+                        }
+                    }
+                }
+                cur_weight = 1u << 20;  // one warp, first in its level
             } else if (op == OP_QUINSEL) {
                 ok = (uint64_t)p + 2 <= c->n_code;
                 const uint32_t N = ok ? code[p + 1] : 0;
@@ -682,7 +760,7 @@ extern "C" int32_t nzcb_circuit_load(nzcb_ctx* ctx, const uint8_t* data, size_t 
             const uint32_t p = ioff_sorted[k];
             const uint32_t op = code[p];
             uint32_t len;
-            if (op == OP_SHAROUND || op == OP_SHASCHED || op == OP_QUINSEL) len = REC_WORDS + 1;  // never a record: code stream
+            if (op == OP_SHAROUND || op == OP_SHASCHED || op == OP_QUINSEL || op == OP_SHABLOCK) len = REC_WORDS + 1;  // never a record: code stream
             else if (op == OP_BITS) len = 4;
             else if (op == OP_INV) len = 3;
             else if (op == OP_BITSLC) len = 3 + 2 + 2 * code[p + 3];

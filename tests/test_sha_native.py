@@ -40,17 +40,22 @@ def _rotr(x, r, n):
     return ((x >> r) | (x << (n - r))) & ((1 << n) - 1) if r else x
 
 
-def _emulate(op, pl, W, nw):
-    """the wires [w0, w0 + size) a word-level step writes, from the witness W (csrc/witness.cu sha_step_warp)"""
-    n, mask = pl["n"], (1 << pl["n"]) - 1
-
+def _words(pl, W, nw):
     def bit(lc):
         v = lc.k
         for w, cf in lc.t.items():
             v += cf * W[w if w >= 0 else nw + (-w - 1)]
         return (v % R) & 1
 
-    x = [sum(bit(b) << i for i, b in enumerate(word)) for word in pl["words"]]
+    return [sum(bit(b) << i for i, b in enumerate(word)) for word in pl["words"]]
+
+
+def _emulate(op, pl, W, nw, x=None):
+    """the wires [w0, w0 + size) a word-level step writes, from the witness W (csrc/witness.cu sha_step_warp);
+    x: the step's input words when they do not come from the witness (inside a block instruction)"""
+    n, mask = pl["n"], (1 << pl["n"]) - 1
+    if x is None:
+        x = _words(pl, W, nw)
     r1a, r1b, r1c = pl["rot1"]
     r0a, r0b, r0c = pl["rot0"]
     out = {}
@@ -99,6 +104,35 @@ def _emulate(op, pl, W, nw):
     return out
 
 
+def _emulate_block(pl, W, nw):
+    """OP_SHABLOCK (csrc/witness.cu sha_block_warp): state and message words gathered once, then the schedule steps
+    and rounds on words, each writing its wires where the per-step instructions would"""
+    from nzcb_circom_b200.circom.builder import OP_SHAROUND as RND, OP_SHASCHED as SCH
+
+    n, mask = pl["n"], (1 << pl["n"]) - 1
+    x = _words(pl, W, nw)
+    a, b, c, d, e, f, g, h = x[:8]
+    w = list(x[8:24])
+    out = {}
+    s_size = 5 * n + 2 - pl["srot1"][2] - pl["srot0"][2]
+    for t in range(pl["r_start"], pl["rounds"]):
+        if t >= 16:
+            st = {"n": n, "rot1": pl["srot1"], "rot0": pl["srot0"], "w0": pl["sched_w0"][t - 16], "size": s_size}
+            o = _emulate(SCH, st, W, nw, [w[t - 2], w[t - 7], w[t - 15], w[t - 16]])
+            out.update(o)
+            o_w = st["w0"] + 4 * n - pl["srot1"][2] - pl["srot0"][2]
+            w.append(sum(o[o_w + i] << i for i in range(n)))
+        rd = {"n": n, "rot1": pl["rot1"], "rot0": pl["rot0"], "K": pl["K"][t - pl["r_start"]],
+              "w0": pl["round_w0"][t - pl["r_start"]], "size": 11 * n + 6}
+        o = _emulate(RND, rd, W, nw, [a, b, c, d, e, f, g, h, w[t]])
+        out.update(o)
+        en = sum(o[rd["w0"] + 9 * n + 4 + i] << i for i in range(n))
+        an = sum(o[rd["w0"] + 10 * n + 5 + i] << i for i in range(n))
+        h, g, f, e = g, f, e, en
+        d, c, b, a = c, b, a, an
+    return out
+
+
 def _msb_bits(data, nbits):
     bits = [(byte >> (7 - k)) & 1 for byte in data for k in range(8)]
     return bits + [0] * (nbits - len(bits))
@@ -117,10 +151,14 @@ def _cases():
 def test_native_steps_reproduce_the_generic_witness():
     for c, cases in _cases():
         art = c.finalize().artifact()
-        fused = [(i[0], i[1]) for i in c.prog if i[0] in (OP_SHAROUND, OP_SHASCHED)]
-        n_round = sum(1 for op, _ in fused if op == OP_SHAROUND)
+        from nzcb_circom_b200.circom.builder import OP_SHABLOCK
+        fused = [(i[0], i[1]) for i in c.prog if i[0] in (OP_SHAROUND, OP_SHASCHED, OP_SHABLOCK)]
+        n_round = sum(1 for op, _ in fused if op == OP_SHAROUND) + \
+            sum(pl["rounds"] - pl["r_start"] for op, pl in fused if op == OP_SHABLOCK)
         # all but the four rounds whose state still holds constants of the initial hash value, per hash call
-        assert n_round >= (2 * 64 - 4 if "256" in c.name else 80 - 4) and len(fused) > n_round
+        assert n_round >= (2 * 64 - 4 if "256" in c.name else 80 - 4)
+        if "256" in c.name:   # both compressions of the two-block SHA-256 are single instructions
+            assert [pl["r_start"] for op, pl in fused if op == OP_SHABLOCK] == [4, 0]
         assert art.n_instr_native < art.n_instr // 8 and art.n_levels_native < art.n_levels // 2
         prog = vm.Program(art.wprog_bytes())
         for inp, digest in cases:
@@ -128,8 +166,9 @@ def test_native_steps_reproduce_the_generic_witness():
             nout = len(digest) * 8
             assert bytes(sum(W[1 + 8 * k + j] << (7 - j) for j in range(8)) for k in range(nout // 8)) == digest
             for op, pl in fused:
-                for w, v in _emulate(op, pl, W, art.n_witness).items():
-                    assert W[w] == v, (c.name, op, pl["w0"], w)
+                got = _emulate_block(pl, W, art.n_witness) if op == OP_SHABLOCK else _emulate(op, pl, W, art.n_witness)
+                for w, v in got.items():
+                    assert W[w] == v, (c.name, op, w)
 
 
 @pytest.mark.gpu
