@@ -404,22 +404,45 @@ def main():
     # the partial sums (128 B per commitment and rank) are all-gathered with NCCL
     split_latency_ms = None
     split_equal = None
+    split_detail = None
     if dist is not None:
         import torch
         from nzcb_circom_b200.sharding import torch_allgather_bytes
         same = pr.marshal_passes(make_passes(0, 0, 1))
         fixed_bl = [list(range(1, 10))]
         ref_proof = pr.prove_raw(same, 1, fixed_bl)[0][0]
+
+        def timed_split():
+            check(pr.prove_raw(same, 1, fixed_bl))  # warm-up (NCCL channel set-up)
+            best = None
+            for _ in range(3):
+                barrier()
+                t0 = time.perf_counter()
+                got = pr.prove_raw(same, 1, fixed_bl)
+                ms = 1000 * max_over_ranks(time.perf_counter() - t0)
+                check(got)
+                best = ms if best is None else min(best, ms)
+            return best, bool(max_over_ranks(0.0 if got[0][0] == ref_proof else 1.0) == 0.0)
+
+        # (a) exchange on the device: the library's own NCCL communicator, partial sums never leave HBM
+        ms_dev = eq_dev = None
+        try:
+            ctx.set_msm_split_nccl(rank, world, dist)
+            ms_dev, eq_dev = timed_split()
+        finally:
+            ctx.set_msm_split_nccl(0, 1)
+        barrier()
+        # (b) the caller-supplied callback (host bounce through torch.distributed): the test shim, kept as a cross-check
         ctx.set_msm_split(rank, world, torch_allgather_bytes(dist, torch.device("cuda", local_rank)))
-        check(pr.prove_raw(same, 1, fixed_bl))  # warm-up (NCCL channel set-up)
-        barrier()
-        t0 = time.perf_counter()
-        got = pr.prove_raw(same, 1, fixed_bl)
-        split_latency_ms = 1000 * max_over_ranks(time.perf_counter() - t0)
+        ms_cb, eq_cb = timed_split()
         ctx.set_msm_split(0, 1, None)
-        check(got)
-        split_equal = bool(max_over_ranks(0.0 if got[0][0] == ref_proof else 1.0) == 0.0)
         barrier()
+        split_latency_ms, split_equal = ms_dev, bool(eq_dev and eq_cb)
+        split_detail = {"exchange": "ncclAllGather on the device (library-owned communicator), sum by a kernel",
+                        "latency_ms_device_exchange": ms_dev, "latency_ms_host_callback_exchange": ms_cb,
+                        "proof_equals_single_gpu": {"device_exchange": eq_dev, "host_callback": eq_cb},
+                        "not_split": "witness program, NTTs, round-3 quotient, digit sort: every rank runs them in full",
+                        "timing": "best of 3 after a warm-up, max over ranks, wall clock around the public call"}
 
     if rank != 0:
         return 0
@@ -496,6 +519,7 @@ def main():
             "roofline_witness": roofline_witness, "whole_proof_roofline": whole,
             "latency_ms_single_proof": latency_ms,
             "latency_ms_single_proof_msm_split": split_latency_ms, "msm_split_proof_equals_single_gpu": split_equal,
+            "msm_split": split_detail,
             "wall_s_device_leg": wall_dev,
             "setup_s": pr.timings}
 

@@ -76,6 +76,15 @@ float nzcb_last_device_ms(const nzcb_ctx* ctx);
 int32_t nzcb_ctx_set_msm_split(nzcb_ctx* ctx, int32_t rank, int32_t world,
                                int (*allgather)(void* user, const void* send, void* recv, size_t bytes), void* user);
 
+/* The same mode with the exchange ON THE DEVICE: the partial sums stay in HBM, `ncclAllGather` runs on the context's
+ * stream over a communicator of the library's own, a kernel adds them up in rank order and only the summed commitment
+ * is read back.  NCCL is not a link-time dependency: `libnccl_path` names the libnccl.so.2 to dlopen (the one torch
+ * bundles; NULL = the loader's search path).  Rank 0 draws the 128-byte id with nzcb_nccl_unique_id and the caller
+ * broadcasts it (any channel); world = 1 turns the mode off and destroys the communicator. */
+int32_t nzcb_nccl_unique_id(const char* libnccl_path, uint8_t id[128]);
+int32_t nzcb_ctx_set_msm_split_nccl(nzcb_ctx* ctx, int32_t rank, int32_t world, const char* libnccl_path,
+                                    const uint8_t id[128]);
+
 /* integer-pipe microbenchmark (roofline denominators): kind 0 = IMAD,
  * 1 = IMAD.WIDE.U32, 2 = Fr Montgomery multiply, 3 = Fq multiply, 4 = IMAD.HI.U32,
  * 5 = Fr multiply, portable CIOS variant; result in ops/s */

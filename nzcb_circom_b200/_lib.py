@@ -73,6 +73,8 @@ SIGNATURES = {
     "nzcb_circuit_free": (None, [_vp]),
     "nzcb_circuit_info": (_i32, [_vp] + [ctypes.POINTER(_u32)] * 3),
     "nzcb_witness_batch": (_i32, [_vp, _vp, _vp, _sz, _vp, _vp]),
+    "nzcb_nccl_unique_id": (_i32, [_cp, _vp]),
+    "nzcb_ctx_set_msm_split_nccl": (_i32, [_vp, _i32, _i32, _cp, _vp]),
     "nzcb_fnv1a64": (ctypes.c_uint64, [_cp, _sz]),
     "nzcb_inputs_resolve": (_i32, [_vp, _sz, _u32, _vp, _vp, _vp, _vp, _vp, _sz]),
     "nzcb_wtns_export": (_i32, [_vp, _u32, _vp, ctypes.POINTER(_sz)]),
@@ -154,6 +156,23 @@ class Context:
         except Exception:
             pass
 
+    def set_msm_split_nccl(self, rank, world, dist=None):
+        """Latency mode with the exchange on the device (nzcb_ctx_set_msm_split_nccl): the library opens its own NCCL
+        communicator; `dist` (torch.distributed, any backend) only carries the 128-byte unique id from rank 0.
+        world <= 1 switches the mode off."""
+        if world <= 1:
+            self.check(self.lib.nzcb_ctx_set_msm_split_nccl(self.h, 0, 1, None, None))
+            return
+        path = nccl_library_path()
+        ids = [None]
+        if rank == 0:
+            buf = (ctypes.c_uint8 * 128)()
+            self.check(self.lib.nzcb_nccl_unique_id(path, buf))
+            ids[0] = bytes(buf)
+        dist.broadcast_object_list(ids, src=0)
+        idbuf = (ctypes.c_uint8 * 128).from_buffer_copy(ids[0])
+        self.check(self.lib.nzcb_ctx_set_msm_split_nccl(self.h, rank, world, path, idbuf))
+
     ALLGATHER_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t)
 
     def set_msm_split(self, rank, world, allgather=None):
@@ -231,6 +250,19 @@ class Context:
         buf = (ctypes.c_uint8 * nbytes)()
         self.check(self.lib.nzcb_dev_download(self.h, buf, p, nbytes))
         return bytes(buf)
+
+
+def nccl_library_path():
+    """the libnccl.so.2 that torch bundles (nvidia-nccl wheel), as bytes for the C ABI; None = loader search path"""
+    try:
+        import nvidia.nccl as _n
+        for base in list(getattr(_n, "__path__", [])) + [os.path.dirname(getattr(_n, "__file__", None) or "")]:
+            p = os.path.join(base, "lib", "libnccl.so.2")
+            if base and os.path.exists(p):
+                return p.encode()
+        return None
+    except Exception:
+        return None
 
 
 def as_cbuf(data):

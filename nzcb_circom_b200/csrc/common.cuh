@@ -32,6 +32,9 @@ struct nzcb_ctx {
     int split_rank = 0, split_world = 1;
     int (*split_allgather)(void* user, const void* send, void* recv, size_t bytes) = nullptr;
     void* split_user = nullptr;
+    // the same exchange on the device: an NCCL communicator of our own (libnccl dlopen'ed at run time, msm.cu);
+    // the partial sums never leave HBM until the summed commitment is read back
+    void* split_nccl_comm = nullptr;
     cudaStream_t stream = nullptr;
     cudaStream_t side = nullptr;         // second stream of this ctx / lane: commitments overlap the transforms of a round
     cudaEvent_t ev_fork = nullptr;

@@ -33,6 +33,7 @@
 // partial sums).   Algorithmic work: n * 16 * 10 modmul in step 4.
 #include "common.cuh"
 #include "msm_affine.cuh"
+#include <dlfcn.h>
 #include <stdlib.h>
 #include <algorithm>
 #include <vector>
@@ -380,8 +381,8 @@ __global__ void __launch_bounds__(128) k_aff_invert(Fq* __restrict__ totals, Fq*
     if (lo >= n_tot) return;
     aff_invert_chunk(totals, tmp, lo, lo + AFF_INV_CHUNK < n_tot ? lo + AFF_INV_CHUNK : n_tot);
 }
-template <bool REFS>
-__global__ void __launch_bounds__(256, 3) k_aff_backward(const G1Affine* __restrict__ pts, const uint32_t* __restrict__ refs,
+template <bool REFS, int CTAS>
+__global__ void __launch_bounds__(256, CTAS) k_aff_backward(const G1Affine* __restrict__ pts, const uint32_t* __restrict__ refs,
                                                          const uint32_t* __restrict__ e_total, uint32_t shift,
                                                          const Fq* __restrict__ P, const Fq* __restrict__ totals_inv,
                                                          G1Affine* __restrict__ out) {
@@ -688,6 +689,10 @@ static int msm_run(nzcb_ctx* ctx, const G1Affine* d_bases, const MsmPlan& p, con
         NZ_CUDA(ctx, cudaEventRecord(ctx->prof_ev[ctx->prof_used].first, ctx->stream));
     }
     const uint32_t* e_total = offsets + n_keys;
+    static const int bwd_ctas = [] {   // resident CTAs per SM of the backward pass: 3 (80 registers) is 4 % faster alone
+        const char* e = getenv("NZCB_AFF_BWD_CTAS");
+        return e && atoi(e) == 2 ? 2 : 3;
+    }();
     for (uint32_t r = 1; r <= R; r++) {
         const size_t adds = (e_max >> r) + 1;           // upper bound; the kernels read the count from e_total
         const unsigned fb = div_up(div_up(adds, AFF_M), 256);
@@ -696,12 +701,14 @@ static int msm_run(nzcb_ctx* ctx, const G1Affine* d_bases, const MsmPlan& p, con
         if (r == 1) {
             NZ_LAUNCH(ctx, k_aff_forward<true>, fb, 256, 0, d_bases, sorted, e_total, r, aff_P, aff_tot);
             NZ_LAUNCH(ctx, k_aff_invert, ib, 128, 0, aff_tot, aff_tmp, e_total, r);
-            NZ_LAUNCH(ctx, k_aff_backward<true>, fb, 256, 0, d_bases, sorted, e_total, r, aff_P, aff_tot, out);
+            if (bwd_ctas == 2) NZ_LAUNCH(ctx, (k_aff_backward<true, 2>), fb, 256, 0, d_bases, sorted, e_total, r, aff_P, aff_tot, out);
+            else NZ_LAUNCH(ctx, (k_aff_backward<true, 3>), fb, 256, 0, d_bases, sorted, e_total, r, aff_P, aff_tot, out);
         } else {
             const G1Affine* in = aff_pts[r & 1];
             NZ_LAUNCH(ctx, k_aff_forward<false>, fb, 256, 0, in, nullptr, e_total, r, aff_P, aff_tot);
             NZ_LAUNCH(ctx, k_aff_invert, ib, 128, 0, aff_tot, aff_tmp, e_total, r);
-            NZ_LAUNCH(ctx, k_aff_backward<false>, fb, 256, 0, in, nullptr, e_total, r, aff_P, aff_tot, out);
+            if (bwd_ctas == 2) NZ_LAUNCH(ctx, (k_aff_backward<false, 2>), fb, 256, 0, in, nullptr, e_total, r, aff_P, aff_tot, out);
+            else NZ_LAUNCH(ctx, (k_aff_backward<false, 3>), fb, 256, 0, in, nullptr, e_total, r, aff_P, aff_tot, out);
         }
     }
     if (R) {
@@ -843,10 +850,67 @@ int msm_to_host_affine(nzcb_ctx* ctx, const G1XYZZ* d_pt, G1Affine* h_out, int c
     return 0;
 }
 
+// ---- latency mode: exchange of the partial sums over NCCL, on the device ------------------------------------
+// libnccl is NOT a link-time dependency: the caller names the library (the one torch bundles) and it is dlopen'ed.
+namespace {
+struct Id128 {  // ncclUniqueId: 128 opaque bytes, passed by value
+    char b[128];
+};
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, Id128, int) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+std::mutex g_nccl_mu;
+int nccl_load(const char* path, char* err, size_t err_len) {
+    std::lock_guard<std::mutex> g(g_nccl_mu);
+    if (g_nccl.lib) return 0;
+    void* h = dlopen(path && path[0] ? path : "libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) {
+        snprintf(err, err_len, "cannot load NCCL (%s): %s", path ? path : "libnccl.so.2", dlerror());
+        return NZCB_E_INVALID;
+    }
+    NcclApi a;
+    a.lib = h;
+    a.GetUniqueId = (int (*)(void*))dlsym(h, "ncclGetUniqueId");
+    a.CommInitRank = (int (*)(void**, int, Id128, int))dlsym(h, "ncclCommInitRank");
+    a.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(h, "ncclAllGather");
+    a.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
+    a.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+    if (!a.GetUniqueId || !a.CommInitRank || !a.AllGather || !a.CommDestroy || !a.GetErrorString) {
+        snprintf(err, err_len, "NCCL library lacks a required symbol");
+        return NZCB_E_INVALID;
+    }
+    g_nccl = a;
+    return 0;
+}
+// out[k] = sum over ranks (in rank order) of all[r * count + k]: every rank adds the same points in the same order
+__global__ void k_sum_partials(const G1XYZZ* __restrict__ all, int world, int count, G1XYZZ* __restrict__ out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    G1XYZZ acc = G1XYZZ::inf();
+    for (int r = 0; r < world; r++) acc.add(all[(size_t)r * count + k]);
+    out[k] = acc;
+}
+}  // namespace
+
 int msm_table_finish(nzcb_ctx* ctx, const G1XYZZ* d_pt, G1Affine* h_out, int count) {
     nzcb_ctx* root = ctx->root();
     if (root->split_world <= 1) return msm_to_host_affine(ctx, d_pt, h_out, count);
     if (count < 1 || count > NZ_MSM_MAXJOBS) return ctx->fail(NZCB_E_INVALID, "msm: bad point count");
+    if (root->split_nccl_comm) {  // device-side exchange: all-gather on this stream, sum by a kernel, one read-back
+        G1XYZZ* d_all = (G1XYZZ*)ctx->scratch_get("msm_split_all", (size_t)root->split_world * NZ_MSM_MAXJOBS * sizeof(G1XYZZ));
+        G1XYZZ* d_sum = (G1XYZZ*)ctx->scratch_get("msm_split_sum", NZ_MSM_MAXJOBS * sizeof(G1XYZZ));
+        if (!d_all || !d_sum) return ctx->fail(NZCB_E_NOMEM, "msm split: out of device memory");
+        const int rc = g_nccl.AllGather(d_pt, d_all, (size_t)count * sizeof(G1XYZZ), /* ncclChar */ 0, root->split_nccl_comm, ctx->stream);
+        if (rc != 0) return ctx->fail(NZCB_E_CUDA, "msm split: ncclAllGather failed: %s", g_nccl.GetErrorString(rc));
+        NZ_LAUNCH(ctx, k_sum_partials, 1, 32, 0, d_all, root->split_world, count, d_sum);
+        return msm_to_host_affine(ctx, d_sum, h_out, count);
+    }
     if (!root->split_allgather) return ctx->fail(NZCB_E_INVALID, "msm split: no exchange function set");
     G1XYZZ mine[NZ_MSM_MAXJOBS];
     NZ_CUDA(ctx, cudaMemcpyAsync(mine, d_pt, (size_t)count * sizeof(G1XYZZ), cudaMemcpyDeviceToHost, ctx->stream));
@@ -866,9 +930,43 @@ int msm_table_finish(nzcb_ctx* ctx, const G1XYZZ* d_pt, G1Affine* h_out, int cou
 
 using namespace nzcb;
 
+extern "C" int32_t nzcb_nccl_unique_id(const char* libnccl_path, uint8_t id[128]) {
+    char err[256];
+    if (!id || nccl_load(libnccl_path, err, sizeof err) != 0) return NZCB_E_INVALID;
+    return g_nccl.GetUniqueId(id) == 0 ? 0 : NZCB_E_CUDA;
+}
+
+extern "C" int32_t nzcb_ctx_set_msm_split_nccl(nzcb_ctx* ctx, int32_t rank, int32_t world, const char* libnccl_path,
+                                               const uint8_t id[128]) {
+    if (!ctx || ctx->parent || world < 1 || rank < 0 || rank >= world) return NZCB_E_INVALID;
+    NZ_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (ctx->split_nccl_comm) {
+        cudaStreamSynchronize(ctx->stream);
+        for (nzcb_ctx* l : ctx->lanes) cudaStreamSynchronize(l->stream);
+        g_nccl.CommDestroy(ctx->split_nccl_comm);
+        ctx->split_nccl_comm = nullptr;
+    }
+    ctx->split_rank = 0;
+    ctx->split_world = 1;
+    ctx->split_allgather = nullptr;
+    if (world == 1) return 0;
+    if (!id) return NZCB_E_INVALID;
+    if (nccl_load(libnccl_path, ctx->err, sizeof ctx->err) != 0) return NZCB_E_INVALID;
+    Id128 uid;
+    memcpy(uid.b, id, 128);
+    void* comm = nullptr;
+    const int rc = g_nccl.CommInitRank(&comm, world, uid, rank);
+    if (rc != 0) return ctx->fail(NZCB_E_CUDA, "ncclCommInitRank failed: %s", g_nccl.GetErrorString(rc));
+    ctx->split_nccl_comm = comm;
+    ctx->split_rank = rank;
+    ctx->split_world = world;
+    return 0;
+}
+
 extern "C" int32_t nzcb_ctx_set_msm_split(nzcb_ctx* ctx, int32_t rank, int32_t world,
                                           int (*allgather)(void*, const void*, void*, size_t), void* user) {
     if (!ctx || ctx->parent || world < 1 || rank < 0 || rank >= world || (world > 1 && !allgather)) return NZCB_E_INVALID;
+    if (ctx->split_nccl_comm) return ctx->fail(NZCB_E_INVALID, "msm split: switch the NCCL mode off first");
     ctx->split_rank = rank;
     ctx->split_world = world;
     ctx->split_allgather = allgather;
