@@ -596,7 +596,9 @@ static int msm_run(nzcb_ctx* ctx, const G1Affine* d_bases, const MsmPlan& p, con
     // halving rounds with batched affine additions first (msm_affine.cuh) when the buckets are full enough for the
     // padding of their segments to multiples of 2^R to be cheap; the XYZZ walk finishes (or does everything, R = 0)
     const size_t e_raw_max = n_sum * p.W;
-    uint32_t R = (!p.sparse && e_raw_max >= 24 * n_keys) ? 3 : 0;
+    // (... and the list long enough: a round is three launches, one of them a 380-multiply Fermat chain of ~0.3 ms
+    // whatever the size -- below ~2^24 entries the XYZZ walk alone is faster: primitive sweep, profiles/)
+    uint32_t R = (!p.sparse && e_raw_max >= 24 * n_keys && e_raw_max >= ((size_t)1 << 24)) ? 3 : 0;
     {
         const char* env = getenv("NZCB_MSM_AFFINE");
         if (env && env[0] >= '0' && env[0] <= '5' && !env[1]) R = (uint32_t)(env[0] - '0');
