@@ -33,7 +33,10 @@ OP_QUINSEL = 9
 # a whole SHA-256 compression from round r_start on (message schedule included): the state stays in registers across
 # the rounds, one level instead of one per round.  Stands for the OP_SHASCHED / OP_SHAROUND steps it is made of.
 OP_SHABLOCK = 10
-FAT_OPS = (OP_SHAROUND, OP_SHASCHED, OP_QUINSEL, OP_SHABLOCK)
+# the rounds of a compression from round r_start on, with the message-schedule words read from their wires (for
+# compressions whose schedule is not regular: constant message bits fold some of its steps away)
+OP_SHAROUNDS = 11
+FAT_OPS = (OP_SHAROUND, OP_SHASCHED, OP_QUINSEL, OP_SHABLOCK, OP_SHAROUNDS)
 
 
 class LC:
@@ -461,7 +464,7 @@ class Compiled:
                 for w in range(pl["w0"], pl["w0"] + pl["size"]):
                     level[w] = l
                 prog.append((op, pl))
-            elif op == OP_SHABLOCK:
+            elif op in (OP_SHABLOCK, OP_SHAROUNDS):
                 pl = dict(ins[1])
                 pl["words"] = [[rlc(b) for b in word] for word in pl["words"]]
                 l = 1 + max((level[w] for word in pl["words"] for b in word for w in b.t), default=0)
@@ -567,6 +570,9 @@ class Compiled:
            SHABLOCK op, n, 12 rotation counts (Sigma1, Sigma0, sigma1, sigma0), r_start, rounds, (rounds - 16) x w0 of
                      the schedule steps, (rounds - r_start) x w0 of the rounds, (rounds - r_start) x K (low word),
                      24 n x <bit> (state a..h at round r_start, message words 0..15), <lc>...  -- native program only
+           SHAROUNDS op, n, 6 rotation counts (Sigma1, Sigma0), r_start, rounds, (rounds - r_start) x w0 of the rounds,
+                     (rounds - r_start) x (K_lo, K_hi), (8 + rounds - r_start) n x <bit> (state a..h at round r_start,
+                     then w[t] for every round), <lc>...  -- native program only
            <bit> = wire id, or 0x80000000 | offset (from the instruction's first word) of the <lc> giving the value
            <lc> = n_terms, const_idx (0xffffffff = no constant), then n_terms x (wire, coef_idx)"""
         consts = {1: 0, R - 1: 1}
@@ -593,7 +599,27 @@ class Compiled:
             ioff.append(len(code))
             op = ins[0]
             code.append(op)
-            if op == OP_SHABLOCK:
+            if op == OP_SHAROUNDS:
+                pl = ins[1]
+                start = ioff[-1]
+                code.append(pl["n"])
+                code.extend(pl["rot1"])
+                code.extend(pl["rot0"])
+                code.extend((pl["r_start"], pl["rounds"]))
+                code.extend(pl["round_w0"])
+                for k in pl["K"]:
+                    code.extend((k & 0xFFFFFFFF, k >> 32))
+                refs = len(code)
+                bits = [b for word in pl["words"] for b in word]
+                code.extend([0] * len(bits))
+                for k, b in enumerate(bits):
+                    w = b.single_wire()
+                    if w is not None:
+                        code[refs + k] = w
+                    else:
+                        code[refs + k] = 0x80000000 | (len(code) - start)
+                        emit_lc(b)
+            elif op == OP_SHABLOCK:
                 pl = ins[1]
                 start = ioff[-1]
                 code.append(pl["n"])

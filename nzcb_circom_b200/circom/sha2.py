@@ -13,7 +13,7 @@ parts of square / cube roots of primes) and pinned by the hashlib cross-checks o
 tests/test_nzcp.py (the digests of real and synthetic passes) and tests/test_sha_native.py."""
 from math import isqrt
 
-from .builder import LC, OP_SHABLOCK, OP_SHAROUND, OP_SHASCHED, Circuit
+from .builder import LC, OP_SHABLOCK, OP_SHAROUND, OP_SHAROUNDS, OP_SHASCHED, Circuit
 from .circomlib import is_equal, num2bits
 
 
@@ -201,6 +201,24 @@ class _Sha2:
                 "K": [self.K[t] for t in range(r_start, self.rounds)],
                 "regions": [sched_w0[t] for t in range(16, self.rounds)] + [round_w0[t] for t in range(r_start, self.rounds)],
                 "words": list(round_state[r_start]) + list(block_words)}, generic))
+        elif r_start is not None and self.rounds - r_start >= 8:
+            # the schedule is not regular (constant message bits) but the rounds are: ONE instruction for all of them,
+            # w[t] read from its wires (or constants) round by round; the schedule keeps its own instructions
+            keep, folded = [], []
+            for ins_ in c.prog[p_block:]:
+                if ins_[0] == OP_SHAROUND and ins_[1]["w0"] >= round_w0[r_start][0]:
+                    folded.append(ins_)
+                else:
+                    keep.append(ins_)
+            generic = [g_ for f_ in folded for g_ in f_[2]]
+            del c.prog[p_block:]
+            c.prog.extend(keep)
+            c.prog.append((OP_SHAROUNDS, {
+                "n": n, "rot1": list(self.big1[:3]), "rot0": list(self.big0[:3]), "r_start": r_start, "rounds": self.rounds,
+                "round_w0": [round_w0[t][0] for t in range(r_start, self.rounds)],
+                "K": [self.K[t] for t in range(r_start, self.rounds)],
+                "regions": [round_w0[t] for t in range(r_start, self.rounds)],
+                "words": list(round_state[r_start]) + [w[t] for t in range(r_start, self.rounds)]}, generic))
         new = [a, b, cc, d, e, f, g, h]
         return [_binsum(c, n, [state[i], new[i]]) for i in range(8)]
 

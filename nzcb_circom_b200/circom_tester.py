@@ -156,6 +156,12 @@ def compile_circuit(name, use_cache=True):
         with open(tmp, "wb") as fh:
             fh.write(zlib.compress(pickle.dumps(art, protocol=4), 1))
         os.replace(tmp, path)
+        for f in os.listdir(_CACHE_DIR):  # build outputs of older builder sources: never read again
+            if f.startswith(key + "-") and f.endswith(".pkz") and f"-{_source_tag()}" not in f:
+                try:
+                    os.remove(os.path.join(_CACHE_DIR, f))
+                except OSError:
+                    pass
     return _compiled[ckey]
 
 

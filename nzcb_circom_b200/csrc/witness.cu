@@ -22,7 +22,7 @@
 
 using namespace nzcb;
 
-enum { OP_LIN = 1, OP_MUL = 2, OP_BITS = 3, OP_INV = 4, OP_ASSERT = 5, OP_BITSLC = 6, OP_SHAROUND = 7, OP_SHASCHED = 8, OP_QUINSEL = 9, OP_SHABLOCK = 10 };
+enum { OP_LIN = 1, OP_MUL = 2, OP_BITS = 3, OP_INV = 4, OP_ASSERT = 5, OP_BITSLC = 6, OP_SHAROUND = 7, OP_SHASCHED = 8, OP_QUINSEL = 9, OP_SHABLOCK = 10, OP_SHAROUNDS = 11 };
 constexpr uint32_t NZ_INV_TAB = 1024;
 constexpr uint32_t NZ_LONG_LC = 24;  // an LC (or bit decomposition) longer than this is evaluated by a whole warp
 
@@ -350,6 +350,28 @@ __device__ __noinline__ void sha_block_warp(const ProgView& pv, Fr* __restrict__
     }
 }
 
+// The rounds of a compression from round r_start on (builder.OP_SHAROUNDS), for compressions whose message schedule
+// keeps its own instructions: the state is gathered once and lives in registers, w[t] is gathered round by round.
+template <class WT, uint32_t TAG>
+__device__ __noinline__ void sha_rounds_warp(const ProgView& pv, Fr* __restrict__ W, uint32_t p, uint32_t lane) {
+    constexpr uint32_t N = ShaWord<WT>::N;
+    const uint32_t* cd = pv.code + p;
+    const uint32_t r_start = cd[8], rounds = cd[9], nr = rounds - r_start;
+    const uint32_t rnd = p + 10, kk = rnd + nr, refs = kk + 2 * nr;
+    WT st[8];
+    sha_gather<WT, 8>(pv, W, p, refs, lane, st);
+    WT a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
+    for (uint32_t i = 0; i < nr; i++) {
+        WT wt;
+        sha_gather<WT, 1>(pv, W, p, refs + (8 + i) * N, lane, &wt);
+        const WT K = (WT)(((uint64_t)pv.code[kk + 2 * i + 1] << 32) | pv.code[kk + 2 * i]);
+        WT en, an;
+        sha_round_emit<WT>(W, pv.code[rnd + i], a, b, c, d, e, f, g, h, wt, K, cd[2], cd[3], cd[4], cd[5], cd[6], cd[7], lane, en, an);
+        h = g; g = f; f = e; e = en;
+        d = c; c = b; b = a; a = an;
+    }
+}
+
 // ---- QuinSelector(N) as one instruction (builder.OP_QUINSEL; circuits/quinSelector.circom:26-41, the GetV of
 // cbortpl.circom:79-90 and every selector of the CBOR walk).  For each choice i the circuit has three signals:
 // eqs[i].inv (IsZero's hint: 1/(i - index) or 0), eqs[i].out (i == index) and sums[i] (the running sum, which is
@@ -426,6 +448,11 @@ __device__ __forceinline__ bool exec_instr(const ProgView& pv, const RD& rd, Fr*
         if (WARP) quinsel_warp<TAG>(pv, W, p, lane);
     } else if (op == OP_SHABLOCK) {
         if (WARP) sha_block_warp<TAG>(pv, W, p, lane);
+    } else if (op == OP_SHAROUNDS) {
+        if (WARP) {
+            if (pv.code[p + 1] == 64) sha_rounds_warp<uint64_t, TAG>(pv, W, p, lane);
+            else sha_rounds_warp<uint32_t, TAG>(pv, W, p, lane);
+        }
     } else if (op == OP_SHAROUND || op == OP_SHASCHED) {
         if (WARP) {
             if (pv.code[p + 1] == 64) sha_step_warp<uint64_t, TAG>(pv, W, p, lane, op);
@@ -666,6 +693,26 @@ extern "C" int32_t nzcb_circuit_load(nzcb_ctx* ctx, const uint8_t* data, size_t 
                 ok = p + 3 <= c->n_code && code[p + 1] < c->n_total && code[p + 2] < c->n_total;
             } else if (op == OP_ASSERT) {
                 p += 1; ok = lc_ok(p) && lc_ok(p) && lc_ok(p);
+            } else if (op == OP_SHAROUNDS) {
+                ok = (uint64_t)p + 10 <= c->n_code && (code[p + 1] == 32 || code[p + 1] == 64);
+                const uint32_t n = ok ? code[p + 1] : 0, r_start = ok ? code[p + 8] : 0, rounds = ok ? code[p + 9] : 0;
+                ok = ok && rounds <= 128 && r_start < rounds;
+                if (ok) {
+                    const uint32_t nr = rounds - r_start, rnd = p + 10, kk = rnd + nr, refs = kk + 2 * nr, n_refs = (8 + nr) * n;
+                    for (uint32_t k = 2; k < 8; k++) ok = ok && code[p + k] < n;
+                    ok = ok && (uint64_t)refs + n_refs <= c->n_code;
+                    for (uint32_t k = 0; ok && k < nr; k++) ok = (uint64_t)code[rnd + k] + 11 * n + 6 <= c->n_total;
+                    for (uint32_t k = 0; ok && k < n_refs; k++) {
+                        const uint32_t ref = code[refs + k];
+                        if (ref & 0x80000000u) {
+                            uint32_t q = p + (ref & 0x7fffffffu);
+                            ok = q >= refs + n_refs && lc_ok(q);
+                        } else {
+                            ok = ref < c->n_total;
+                        }
+                    }
+                }
+                cur_weight = 1u << 20;  // one warp, first in its level
             } else if (op == OP_SHABLOCK) {
                 ok = (uint64_t)p + 16 <= c->n_code && code[p + 1] == 32;
                 const uint32_t r_start = ok ? code[p + 14] : 0, rounds = ok ? code[p + 15] : 0;
@@ -760,7 +807,7 @@ extern "C" int32_t nzcb_circuit_load(nzcb_ctx* ctx, const uint8_t* data, size_t 
             const uint32_t p = ioff_sorted[k];
             const uint32_t op = code[p];
             uint32_t len;
-            if (op == OP_SHAROUND || op == OP_SHASCHED || op == OP_QUINSEL || op == OP_SHABLOCK) len = REC_WORDS + 1;  // never a record: code stream
+            if (op == OP_SHAROUND || op == OP_SHASCHED || op == OP_QUINSEL || op == OP_SHABLOCK || op == OP_SHAROUNDS) len = REC_WORDS + 1;  // never a record: code stream
             else if (op == OP_BITS) len = 4;
             else if (op == OP_INV) len = 3;
             else if (op == OP_BITSLC) len = 3 + 2 + 2 * code[p + 3];

@@ -133,6 +133,25 @@ def _emulate_block(pl, W, nw):
     return out
 
 
+def _emulate_rounds(pl, W, nw):
+    """OP_SHAROUNDS (csrc/witness.cu sha_rounds_warp): state gathered once, w[t] read round by round"""
+    from nzcb_circom_b200.circom.builder import OP_SHAROUND as RND
+
+    n = pl["n"]
+    x = _words(pl, W, nw)
+    a, b, c, d, e, f, g, h = x[:8]
+    out = {}
+    for i in range(pl["rounds"] - pl["r_start"]):
+        rd = {"n": n, "rot1": pl["rot1"], "rot0": pl["rot0"], "K": pl["K"][i], "w0": pl["round_w0"][i], "size": 11 * n + 6}
+        o = _emulate(RND, rd, W, nw, [a, b, c, d, e, f, g, h, x[8 + i]])
+        out.update(o)
+        en = sum(o[rd["w0"] + 9 * n + 4 + k] << k for k in range(n))
+        an = sum(o[rd["w0"] + 10 * n + 5 + k] << k for k in range(n))
+        h, g, f, e = g, f, e, en
+        d, c, b, a = c, b, a, an
+    return out
+
+
 def _msb_bits(data, nbits):
     bits = [(byte >> (7 - k)) & 1 for byte in data for k in range(8)]
     return bits + [0] * (nbits - len(bits))
@@ -151,14 +170,16 @@ def _cases():
 def test_native_steps_reproduce_the_generic_witness():
     for c, cases in _cases():
         art = c.finalize().artifact()
-        from nzcb_circom_b200.circom.builder import OP_SHABLOCK
-        fused = [(i[0], i[1]) for i in c.prog if i[0] in (OP_SHAROUND, OP_SHASCHED, OP_SHABLOCK)]
+        from nzcb_circom_b200.circom.builder import OP_SHABLOCK, OP_SHAROUNDS
+        fused = [(i[0], i[1]) for i in c.prog if i[0] in (OP_SHAROUND, OP_SHASCHED, OP_SHABLOCK, OP_SHAROUNDS)]
         n_round = sum(1 for op, _ in fused if op == OP_SHAROUND) + \
-            sum(pl["rounds"] - pl["r_start"] for op, pl in fused if op == OP_SHABLOCK)
+            sum(pl["rounds"] - pl["r_start"] for op, pl in fused if op in (OP_SHABLOCK, OP_SHAROUNDS))
         # all but the four rounds whose state still holds constants of the initial hash value, per hash call
         assert n_round >= (2 * 64 - 4 if "256" in c.name else 80 - 4)
         if "256" in c.name:   # both compressions of the two-block SHA-256 are single instructions
             assert [pl["r_start"] for op, pl in fused if op == OP_SHABLOCK] == [4, 0]
+        else:                 # SHA-512's padded block: the schedule keeps its steps, the 76 regular rounds are one instruction
+            assert [(pl["n"], pl["r_start"]) for op, pl in fused if op == OP_SHAROUNDS] == [(64, 4)]
         assert art.n_instr_native < art.n_instr // 8 and art.n_levels_native < art.n_levels // 2
         prog = vm.Program(art.wprog_bytes())
         for inp, digest in cases:
@@ -166,7 +187,8 @@ def test_native_steps_reproduce_the_generic_witness():
             nout = len(digest) * 8
             assert bytes(sum(W[1 + 8 * k + j] << (7 - j) for j in range(8)) for k in range(nout // 8)) == digest
             for op, pl in fused:
-                got = _emulate_block(pl, W, art.n_witness) if op == OP_SHABLOCK else _emulate(op, pl, W, art.n_witness)
+                got = (_emulate_block(pl, W, art.n_witness) if op == OP_SHABLOCK else
+                       _emulate_rounds(pl, W, art.n_witness) if op == OP_SHAROUNDS else _emulate(op, pl, W, art.n_witness))
                 for w, v in got.items():
                     assert W[w] == v, (c.name, op, w)
 
