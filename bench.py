@@ -380,7 +380,7 @@ def main():
         w_ms = ctx.last_device_ms
         ctx.dev_free(d_w_in)
         w_bytes = float(pr.art.n_total) * 32 * nbw
-        roofline_witness = {"bound": "hbm", "kernel": "k_witness (level-scheduled witness program)", "unit": "GB/s",
+        roofline_witness = {"bound": "hbm", "kernel": "k_witness (level-scheduled witness program with word-level SHA-2 / QuinSelector instructions)", "unit": "GB/s",
                             "achieved": w_bytes / (w_ms / 1000.0) / 1e9, "peak": None, "frac": None,
                             "passes": nbw, "ms": w_ms, "passes_per_s": nbw / (w_ms / 1000.0),
                             "algorithmic_unit": f"nTotal x 32 B written per pass = {pr.art.n_total * 32} B (SURVEY.md 8d)",

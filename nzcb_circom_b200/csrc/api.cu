@@ -77,6 +77,7 @@ extern "C" void nzcb_ctx_free(nzcb_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (nzcb_ctx* l : ctx->lanes) nzcb_ctx_free(l);
     ctx->lanes.clear();
+    nzcb::msm_split_release(ctx);
     for (auto& kv : ctx->twiddles) cudaFree(kv.second);
     for (auto& kv : ctx->scratch)
         if (kv.second.first) cudaFree(kv.second.first);

@@ -141,5 +141,7 @@ int g1_lagrange_basis(nzcb_ctx* ctx, const G1Affine* d_srs, uint32_t log_n, G1Af
 int msm_to_host_affine(nzcb_ctx* ctx, const G1XYZZ* d_pt, G1Affine* h_out, int count = 1);
 // the same for results of msm_table_dev: in latency mode the ranks' partial sums are exchanged and added first
 int msm_table_finish(nzcb_ctx* ctx, const G1XYZZ* d_pt, G1Affine* h_out, int count);
+// destroys the latency mode's NCCL communicator of a context that is being freed (no-op otherwise)
+void msm_split_release(nzcb_ctx* ctx);
 
 }  // namespace nzcb

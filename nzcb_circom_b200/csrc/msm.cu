@@ -900,6 +900,12 @@ __global__ void k_sum_partials(const G1XYZZ* __restrict__ all, int world, int co
 }
 }  // namespace
 
+// called when a context goes away: the latency mode's communicator is the library's own
+void msm_split_release(nzcb_ctx* ctx) {
+    if (ctx && ctx->split_nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->split_nccl_comm);
+    if (ctx) ctx->split_nccl_comm = nullptr;
+}
+
 int msm_table_finish(nzcb_ctx* ctx, const G1XYZZ* d_pt, G1Affine* h_out, int count) {
     nzcb_ctx* root = ctx->root();
     if (root->split_world <= 1) return msm_to_host_affine(ctx, d_pt, h_out, count);
