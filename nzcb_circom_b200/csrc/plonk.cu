@@ -893,13 +893,13 @@ int prove_core(nzcb_ctx* ctx, const nzcb_zkey* zk, const Fr* d_w_le, const uint8
     const Fr wn = fr_root_host(zk->power);
     const Fr xiw = xi * wn;
     // vals: 1 eval_a, 2 eval_b, 3 eval_c, 4 eval_s1, 5 eval_s2, 6 eval_t, 7 eval_zw, 8 eval_r, 9/10 remainders
-    NZ_TRY(poly_horner(ctx, b.pol_a, N + 2, xi, b.vals + 1, nullptr));
-    NZ_TRY(poly_horner(ctx, b.pol_b, N + 2, xi, b.vals + 2, nullptr));
-    NZ_TRY(poly_horner(ctx, b.pol_c, N + 2, xi, b.vals + 3, nullptr));
-    NZ_TRY(poly_horner(ctx, S1, N, xi, b.vals + 4, nullptr));
-    NZ_TRY(poly_horner(ctx, S2, N, xi, b.vals + 5, nullptr));
-    NZ_TRY(poly_horner(ctx, pol_t, 3 * N + 6, xi, b.vals + 6, nullptr));
-    NZ_TRY(poly_horner(ctx, b.pol_z, N + 3, xiw, b.vals + 7, nullptr));
+    {   // the seven evaluations of round 4 in one chain of launches (they are independent)
+        const Fr* ps[7] = {b.pol_a, b.pol_b, b.pol_c, S1, S2, pol_t, b.pol_z};
+        const size_t ns[7] = {N + 2, N + 2, N + 2, N, N, 3 * N + 6, N + 3};
+        const Fr at[7] = {xi, xi, xi, xi, xi, xi, xiw};
+        Fr* vs[7] = {b.vals + 1, b.vals + 2, b.vals + 3, b.vals + 4, b.vals + 5, b.vals + 6, b.vals + 7};
+        NZ_TRY(poly_horner_multi(ctx, 7, ps, ns, at, vs));
+    }
     Fr ev[16];
     NZ_CUDA(ctx, cudaMemcpyAsync(ev, b.vals, 8 * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
     NZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -84,6 +84,80 @@ int poly_horner(nzcb_ctx* ctx, const Fr* d_p, size_t n, const Fr& x, Fr* d_value
     return 0;
 }
 
+// Several evaluations at once (round 4 evaluates seven polynomials): the up-sweeps of all of them share one launch per
+// level (blockIdx.y = polynomial) instead of running one latency-bound chain of launches after the other.
+struct HornerMulti {
+    const Fr* in[NZ_HORNER_MAX];
+    Fr* out[NZ_HORNER_MAX];
+    size_t n_in[NZ_HORNER_MAX], n_out[NZ_HORNER_MAX];
+    Fr x[NZ_HORNER_MAX];
+};
+__global__ void __launch_bounds__(128) k_horner_up_multi(HornerMulti a) {
+    const int k = blockIdx.y;
+    const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= a.n_out[k]) return;
+    const size_t lo = s * NZ_SEG;
+    size_t hi = lo + NZ_SEG;
+    if (hi > a.n_in[k]) hi = a.n_in[k];
+    const Fr* in = a.in[k];
+    const Fr x = a.x[k];
+    Fr acc = Fr::zero();
+    for (size_t i = hi; i > lo; i--) acc = acc * x + in[i - 1];
+    a.out[k][s] = acc;
+}
+
+int poly_horner_multi(nzcb_ctx* ctx, int K, const Fr* const* d_p, const size_t* n, const Fr* x, Fr* const* d_value) {
+    if (K < 1 || K > NZ_HORNER_MAX) return ctx->fail(NZCB_E_INVALID, "poly_horner_multi: 1..%d polynomials", NZ_HORNER_MAX);
+    // level sizes per polynomial; all scratch in one arena
+    std::vector<std::vector<size_t>> len(K);
+    size_t total = 0;
+    int top_max = 0;
+    for (int k = 0; k < K; k++) {
+        if (n[k] == 0) return ctx->fail(NZCB_E_INVALID, "poly_horner_multi: empty polynomial");
+        len[k].push_back(n[k]);
+        while (len[k].back() > 1) len[k].push_back((len[k].back() + NZ_SEG - 1) / NZ_SEG);
+        for (size_t l = 1; l < len[k].size(); l++) total += len[k][l];
+        top_max = std::max(top_max, (int)len[k].size() - 1);
+    }
+    Fr* up = (Fr*)ctx->scratch_get("horner_multi_up", (total + 1) * sizeof(Fr));
+    if (!up) return ctx->fail(NZCB_E_NOMEM, "poly_horner_multi: out of device memory");
+    std::vector<const Fr*> cur(K);
+    std::vector<Fr> xs(x, x + K);
+    std::vector<int> level(K, 0);
+    for (int k = 0; k < K; k++) cur[k] = d_p[k];
+    size_t off = 0;
+    for (int l = 0; l < top_max; l++) {
+        HornerMulti a;
+        memset(&a, 0, sizeof(a));
+        size_t widest = 0;
+        for (int k = 0; k < K; k++) {
+            const int top = (int)len[k].size() - 1;
+            if (l >= top) {  // this polynomial is done: nothing to do at this level
+                a.n_out[k] = 0;
+                continue;
+            }
+            a.in[k] = cur[k];
+            a.n_in[k] = len[k][l];
+            a.n_out[k] = len[k][l + 1];
+            a.out[k] = up + off;
+            a.x[k] = xs[k];
+            off += len[k][l + 1];
+            widest = std::max(widest, a.n_out[k]);
+        }
+        NZ_LAUNCH(ctx, k_horner_up_multi, dim3(div_up(widest, 128), (unsigned)K), 128, 0, a);
+        for (int k = 0; k < K; k++) {
+            if (a.n_out[k] == 0) continue;
+            cur[k] = a.out[k];
+            Fr t = xs[k];
+            for (int q = 0; q < 6; q++) t = t.sqr();  // x^(SEG), SEG = 64
+            xs[k] = t;
+        }
+    }
+    for (int k = 0; k < K; k++)  // single-coefficient polynomials: value = p[0]
+        NZ_CUDA(ctx, cudaMemcpyAsync(d_value[k], cur[k], sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->stream));
+    return 0;
+}
+
 __global__ void __launch_bounds__(128) k_prod_up(const Fr* __restrict__ in, size_t n_in, Fr* __restrict__ out, size_t n_out) {
     const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_out) return;

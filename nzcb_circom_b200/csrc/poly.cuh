@@ -15,6 +15,10 @@ constexpr int NZ_SEG = 64;  // elements one thread walks sequentially in a scan 
 // d_value: device Fr receiving p(x);  d_quot: nullptr or n elements.
 int poly_horner(nzcb_ctx* ctx, const Fr* d_p, size_t n, const Fr& x, Fr* d_value, Fr* d_quot);
 
+// K <= NZ_HORNER_MAX evaluations p_k(x_k) with one launch per level for all of them (values only, no quotient)
+constexpr int NZ_HORNER_MAX = 8;
+int poly_horner_multi(nzcb_ctx* ctx, int K, const Fr* const* d_p, const size_t* n, const Fr* x, Fr* const* d_value);
+
 // exclusive prefix product: out[i] = prod_{j<i} in[j]; *d_total = prod of all.  in == out allowed.
 int prefix_product(nzcb_ctx* ctx, const Fr* d_in, size_t n, Fr* d_out, Fr* d_total);
 
