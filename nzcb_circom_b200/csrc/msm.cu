@@ -146,6 +146,45 @@ __global__ void __launch_bounds__(256) k_msm_digits(DigitArgs a, uint32_t* __res
     if (neg) s = Fr::modulus() - s;
     uint32_t carry = 0;
     const uint32_t half = 1u << (a.c - 1);
+    if (!AGG) {
+        // dense scalars: no lane cooperation, so four digits at a time -- their atomics (and the offset loads) are
+        // in flight together before the first reference is stored: one memory round trip per four digits, not four
+        for (uint32_t w0 = 0; w0 < a.W; w0 += 4) {
+            uint32_t key[4], ref[4], base[4], off[4];
+            bool has[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t w = w0 + u;
+                has[u] = false;
+                if (w >= a.W) continue;
+                uint32_t d = get_bits(s.v, w * a.c, a.c) + carry;
+                bool dneg = false;
+                if (d > half) {
+                    carry = 1;
+                    d = (1u << a.c) - d;
+                    dneg = true;
+                } else {
+                    carry = 0;
+                }
+                has[u] = live && d != 0;
+                const uint32_t set = a.unified ? k : k * a.W + w;
+                key[u] = set * a.nbw + (d - 1);
+                ref[u] = (a.unified ? w * a.stride + i : i) | ((neg != dneg) ? 0x80000000u : 0u);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (has[u]) {
+                    base[u] = atomicAdd(&cnt[key[u]], 1u);
+                    if (!COUNT) off[u] = offsets[key[u]];
+                }
+            if (!COUNT) {
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (has[u]) sorted[off[u] + base[u]] = ref[u];
+            }
+        }
+        return;
+    }
     for (uint32_t w = 0; w < a.W; w++) {
         uint32_t d = get_bits(s.v, w * a.c, a.c) + carry;
         bool dneg = false;

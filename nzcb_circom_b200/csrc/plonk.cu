@@ -228,23 +228,26 @@ __global__ void __launch_bounds__(256) k_rowcheck(RowArgs q) {
 struct R3Args {
     const Fr *A, *B, *C, *Z;  // blinded a, b, c, z on the coset (4n values each)
     const Fr *QM, *QL, *QR, *QO, *QC, *S1, *S2, *S3, *LAG, *pub, *W4n;
-    Fr g, beta, gamma, alpha, alpha2, k1, k2;
+    Fr g, beta, beta_g, gamma, alpha, alpha2, k1, k2;
     Fr zh_inv[4];
-    uint32_t n, power, n_pub;
+    uint32_t n, power, n_pub, k_small;  // k_small: k1 == 2 and k2 == 3
     Fr* T;
 };
 __global__ void __launch_bounds__(128) k_round3(R3Args q) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t n4 = (size_t)4 * q.n;
     if (i >= n4) return;
-    const Fr x = domain_pow(q.W4n, q.power + 2, i) * q.g;
     const Fr a = q.A[i], b = q.B[i], c = q.C[i], z = q.Z[i];
     const Fr zw = q.Z[(i + 4) & (n4 - 1)];
     Fr pl = Fr::zero();
     for (uint32_t j = 0; j < q.n_pub; j++) pl = pl - q.LAG[(size_t)j * n4 + i] * q.pub[j];
     const Fr gate = (a * b) * q.QM[i] + a * q.QL[i] + b * q.QR[i] + c * q.QO[i] + q.QC[i] + pl;
-    const Fr bx = q.beta * x;
-    const Fr p1 = ((a + bx + q.gamma) * (b + bx * q.k1 + q.gamma)) * ((c + bx * q.k2 + q.gamma) * z);
+    // beta * x with x = g w^i: one product with the host's beta * g; k1 = 2, k2 = 3 (every power snarkjs supports
+    // here) turn the two other coset shifts into additions
+    const Fr bx = q.beta_g * domain_pow(q.W4n, q.power + 2, i);
+    const Fr bx2 = q.k_small ? bx + bx : bx * q.k1;
+    const Fr bx3 = q.k_small ? bx2 + bx : bx * q.k2;
+    const Fr p1 = ((a + bx + q.gamma) * (b + bx2 + q.gamma)) * ((c + bx3 + q.gamma) * z);
     const Fr p2 = ((a + q.beta * q.S1[i] + q.gamma) * (b + q.beta * q.S2[i] + q.gamma)) *
                   ((c + q.beta * q.S3[i] + q.gamma) * zw);
     const Fr l1 = (z - Fr::one()) * q.LAG[i] * q.alpha2;
@@ -856,6 +859,8 @@ int prove_core(nzcb_ctx* ctx, const nzcb_zkey* zk, const Fr* d_w_le, const uint8
         g.QM = zk->d_cos[0]; g.QL = zk->d_cos[1]; g.QR = zk->d_cos[2]; g.QO = zk->d_cos[3]; g.QC = zk->d_cos[4];
         g.S1 = zk->d_cos[5]; g.S2 = zk->d_cos[6]; g.S3 = zk->d_cos[7]; g.LAG = zk->d_cos_lag; g.pub = b.pub; g.W4n = W4n;
         g.g = zk->g; g.beta = beta; g.gamma = gamma; g.alpha = alpha; g.alpha2 = alpha2; g.k1 = zk->k1; g.k2 = zk->k2;
+        g.beta_g = beta * zk->g;
+        g.k_small = (zk->k1 == Fr::from_u64(2) && zk->k2 == Fr::from_u64(3)) ? 1u : 0u;
         for (int i = 0; i < 4; i++) g.zh_inv[i] = zk->zh_inv[i];
         g.n = n; g.power = zk->power; g.n_pub = n_pub; g.T = b.T;
         NZ_LAUNCH(ctx, k_round3, div_up(4 * N, 128), 128, 0, g);
