@@ -78,6 +78,11 @@ extern "C" void nzcb_ctx_free(nzcb_ctx* ctx) {
     for (nzcb_ctx* l : ctx->lanes) nzcb_ctx_free(l);
     ctx->lanes.clear();
     nzcb::msm_split_release(ctx);
+    for (int b = 0; b < 2; b++) {
+        if (ctx->wt_pin[b]) cudaFreeHost(ctx->wt_pin[b]);
+        if (ctx->wt_ev[b]) cudaEventDestroy(ctx->wt_ev[b]);
+    }
+    if (ctx->wt_copy) cudaStreamDestroy(ctx->wt_copy);
     for (auto& kv : ctx->twiddles) cudaFree(kv.second);
     for (auto& kv : ctx->scratch)
         if (kv.second.first) cudaFree(kv.second.first);

@@ -35,6 +35,12 @@ struct nzcb_ctx {
     // the same exchange on the device: an NCCL communicator of our own (libnccl dlopen'ed at run time, msm.cu);
     // the partial sums never leave HBM until the summed commitment is read back
     void* split_nccl_comm = nullptr;
+    // large witness batches from host memory: pinned staging pair + copy stream, so that the upload of chunk k + 1
+    // (host memcpy into pinned memory, then DMA) overlaps the witness kernel of chunk k.  Root only, grow-only.
+    void* wt_pin[2] = {nullptr, nullptr};
+    size_t wt_pin_bytes = 0;
+    cudaStream_t wt_copy = nullptr;
+    cudaEvent_t wt_ev[2] = {nullptr, nullptr};
     cudaStream_t stream = nullptr;
     cudaStream_t side = nullptr;         // second stream of this ctx / lane: commitments overlap the transforms of a round
     cudaEvent_t ev_fork = nullptr;

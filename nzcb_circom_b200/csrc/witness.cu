@@ -996,24 +996,65 @@ static int32_t witness_batch_ex_impl(nzcb_ctx* ctx, const nzcb_circuit* c, const
     const size_t per_pass = (size_t)c->n_total * sizeof(Fr);
     const size_t chunk = witness_chunk(ctx, per_pass, B);
     Fr* d_w = (Fr*)ctx->scratch_get("wt_wires", chunk * per_pass);
-    Fr* d_in = (Fr*)ctx->scratch_get("wt_inputs", std::max<size_t>(32, chunk * (size_t)c->n_in * sizeof(Fr)));
+    const size_t in_bytes = std::max<size_t>(32, chunk * (size_t)c->n_in * sizeof(Fr));
+    Fr* d_in2[2] = {(Fr*)ctx->scratch_get("wt_inputs", in_bytes), nullptr};
     int32_t* d_st = (int32_t*)ctx->scratch_get("wt_status", chunk * sizeof(int32_t));
     uint64_t* d_dg = (uint64_t*)ctx->scratch_get("wt_digest", chunk * sizeof(uint64_t));
-    if (!d_w || !d_in || !d_st || !d_dg) return ctx->fail(NZCB_E_NOMEM, "witness: cannot allocate %zu device bytes", chunk * per_pass);
+    if (!d_w || !d_in2[0] || !d_st || !d_dg) return ctx->fail(NZCB_E_NOMEM, "witness: cannot allocate %zu device bytes", chunk * per_pass);
+    // Host inputs of a batch longer than one chunk: chunk k + 1 is staged (host memcpy into pinned memory, DMA on a copy
+    // stream into the second input buffer) while chunk k's kernel runs; a single chunk is copied straight from the caller.
+    const bool staged = !inputs_on_device && c->n_in && B > chunk;
+    if (staged) {
+        d_in2[1] = (Fr*)ctx->scratch_get("wt_inputs_b", in_bytes);
+        if (!d_in2[1]) return ctx->fail(NZCB_E_NOMEM, "witness: cannot allocate the second input buffer");
+        if (ctx->wt_pin_bytes < in_bytes) {
+            for (int b = 0; b < 2; b++) {
+                if (ctx->wt_pin[b]) cudaFreeHost(ctx->wt_pin[b]);
+                ctx->wt_pin[b] = nullptr;
+            }
+            ctx->wt_pin_bytes = 0;
+            if (cudaHostAlloc(&ctx->wt_pin[0], in_bytes, cudaHostAllocDefault) != cudaSuccess ||
+                cudaHostAlloc(&ctx->wt_pin[1], in_bytes, cudaHostAllocDefault) != cudaSuccess) {
+                cudaGetLastError();
+                return ctx->fail(NZCB_E_NOMEM, "witness: cannot allocate %zu bytes of pinned staging memory", 2 * in_bytes);
+            }
+            ctx->wt_pin_bytes = in_bytes;
+        }
+        if (!ctx->wt_copy) NZ_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->wt_copy, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; b++)
+            if (!ctx->wt_ev[b]) NZ_CUDA(ctx, cudaEventCreateWithFlags(&ctx->wt_ev[b], cudaEventDisableTiming));
+    }
+    // stage(k): inputs of chunk k -> pinned[k & 1] -> d_in2[k & 1] on the copy stream; the event marks its arrival.
+    // Both buffers of parity k & 1 were last used by chunk k - 2, whose kernel and copy are complete (see the loop).
+    auto stage = [&](size_t k) -> int {
+        const size_t lo = k * chunk, nbk = std::min(chunk, B - lo), bytes = nbk * (size_t)c->n_in * 32;
+        const int b = (int)(k & 1);
+        memcpy(ctx->wt_pin[b], inputs_le + lo * (size_t)c->n_in * 32, bytes);
+        NZ_CUDA(ctx, cudaMemcpyAsync(d_in2[b], ctx->wt_pin[b], bytes, cudaMemcpyHostToDevice, ctx->wt_copy));
+        NZ_CUDA(ctx, cudaEventRecord(ctx->wt_ev[b], ctx->wt_copy));
+        return 0;
+    };
     NZ_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-    for (size_t done = 0; done < B; done += chunk) {
+    if (staged) NZ_TRY(stage(0));
+    for (size_t done = 0, k = 0; done < B; done += chunk, k++) {
         const size_t nb = std::min(chunk, B - done);
-        const Fr* cur_in = d_in;
+        const Fr* cur_in = d_in2[0];
         if (inputs_on_device) cur_in = reinterpret_cast<const Fr*>(inputs_le) + done * (size_t)c->n_in;
-        else if (c->n_in)
-            NZ_CUDA(ctx, cudaMemcpyAsync(d_in, inputs_le + done * (size_t)c->n_in * 32, nb * (size_t)c->n_in * 32,
+        else if (staged) {
+            cur_in = d_in2[k & 1];
+            NZ_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->wt_ev[k & 1], 0));
+        } else if (c->n_in)
+            NZ_CUDA(ctx, cudaMemcpyAsync(d_in2[0], inputs_le + done * (size_t)c->n_in * 32, nb * (size_t)c->n_in * 32,
                                          cudaMemcpyHostToDevice, ctx->stream));
         NZ_TRY(witness_dev(ctx, c, cur_in, nb, d_w, d_st));
+        if (digest) NZ_LAUNCH(ctx, k_witness_digest, (unsigned)nb, 256, 0, d_w, c->n_total, c->n_witness, d_dg);
+        // the next chunk's inputs travel while this chunk's kernel runs: staged BEFORE the read-backs below, which block
+        // the host until the kernel is done (device-to-pageable copies are synchronous for the host).  Its buffers were
+        // last used by chunk k - 1, complete since the previous iteration's synchronisation.
+        if (staged && done + chunk < B) NZ_TRY(stage(k + 1));
         NZ_CUDA(ctx, cudaMemcpyAsync(status + done, d_st, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-        if (digest) {
-            NZ_LAUNCH(ctx, k_witness_digest, (unsigned)nb, 256, 0, d_w, c->n_total, c->n_witness, d_dg);
+        if (digest)
             NZ_CUDA(ctx, cudaMemcpyAsync(digest + done, d_dg, nb * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
-        }
         if (outputs_le && c->n_out)
             NZ_CUDA(ctx, cudaMemcpy2DAsync(outputs_le + done * (size_t)c->n_out * 32, (size_t)c->n_out * 32, d_w + 1, per_pass,
                                            (size_t)c->n_out * 32, nb, cudaMemcpyDeviceToHost, ctx->stream));
