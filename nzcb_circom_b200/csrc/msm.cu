@@ -183,9 +183,8 @@ __global__ void __launch_bounds__(256) k_msm_digits(DigitArgs a, uint32_t* __res
                     if (has[u]) sorted[off[u] + base[u]] = ref[u];
             }
         }
-        return;
     }
-    for (uint32_t w = 0; w < a.W; w++) {
+    for (uint32_t w = 0; AGG && w < a.W; w++) {
         uint32_t d = get_bits(s.v, w * a.c, a.c) + carry;
         bool dneg = false;
         if (d > half) {
