@@ -165,11 +165,13 @@ class Context:
             return
         path = nccl_library_path()
         ids = [None]
-        if rank == 0:
+        if rank == 0:  # a failure here is broadcast too, so that no rank is left waiting in the collective
             buf = (ctypes.c_uint8 * 128)()
-            self.check(self.lib.nzcb_nccl_unique_id(path, buf))
-            ids[0] = bytes(buf)
+            if self.lib.nzcb_nccl_unique_id(path, buf) == 0:
+                ids[0] = bytes(buf)
         dist.broadcast_object_list(ids, src=0)
+        if ids[0] is None:
+            raise NzcbError(NZCB_E_INVALID, f"cannot load NCCL ({path!r}) for the device-side exchange")
         idbuf = (ctypes.c_uint8 * 128).from_buffer_copy(ids[0])
         self.check(self.lib.nzcb_ctx_set_msm_split_nccl(self.h, rank, world, path, idbuf))
 
