@@ -273,3 +273,40 @@ def test_witness_batch_65536_passes(ctx):
     assert len(oracle_digest) >= 8 and len(pub_seen) == D
     print(f"65,536 passes in {total_ms:.0f} ms of device time ({65536 / total_ms * 1e3:.0f} passes/s), "
           f"{len(oracle_digest)} witnesses compared wire for wire with the C oracle")
+
+
+def test_witness_batch_device_resident_inputs_equal_host_inputs(ctx):
+    """nzcb_witness_batch_ex_dev (inputs already in HBM: bench.py's roofline_witness) against nzcb_witness_batch_ex
+    (host inputs; more than one launch, so the staged upload runs): same status, public outputs and all-wire digests"""
+    import ctypes
+
+    from nzcb_circom_b200.circom_tester import wasm_tester
+
+    cir = wasm_tester("nzcp_live", ctx)
+    art = cir.compiled
+    B = 1000  # > one wave of 888 passes: two launches
+    rows = []
+    for s_ in range(40):
+        p = H.synth_pass(900 + s_)
+        vals = art.flatten_input(H.nzcp_input(p["toBeSigned"], 351, p["data"]))
+        rows.append(b"".join(int(v).to_bytes(32, "little") for v in vals))
+    bad = bytearray(rows[3])
+    bad[0:32] = (2).to_bytes(32, "little")
+    buf = b"".join(bytes(bad) if i == 777 else rows[i % 40] for i in range(B))
+    h = cir._handle(ctx)
+    res = []
+    d = ctx.dev_alloc(len(buf))
+    ctx.dev_upload(d, buf)
+    for dev in (False, True):
+        status = (ctypes.c_int32 * B)()
+        outputs = ctypes.create_string_buffer(B * art.n_out * 32)
+        digest = (ctypes.c_uint64 * B)()
+        fn = ctx.lib.nzcb_witness_batch_ex_dev if dev else ctx.lib.nzcb_witness_batch_ex
+        ctx.check(fn(ctx.h, h, d if dev else buf, B, outputs, digest, 0, None, status))
+        res.append((list(status), outputs.raw, list(digest)))
+    ctx.dev_free(d)
+    assert res[0][0] == res[1][0] and [i for i, s_ in enumerate(res[0][0]) if s_ != 0] == [777]
+    keep = [i for i in range(B) if i != 777]
+    assert all(res[0][2][i] == res[1][2][i] for i in keep) and all(res[0][2][i] == res[0][2][i % 40] for i in keep if i % 40 != 777 % 40 or True)
+    n = art.n_out * 32
+    assert all(res[0][1][i * n:(i + 1) * n] == res[1][1][i * n:(i + 1) * n] for i in keep)
