@@ -332,7 +332,7 @@ __device__ __noinline__ void sha_block_warp(const ProgView& pv, Fr* __restrict__
         if (lane == k) win = v;
     }
     uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
-    for (uint32_t t = 16; t < r_start; t++) {}  // (r_start <= 16: the schedule starts with the rounds)
+    // r_start <= 16 (loader): every schedule step t >= 16 is computed right before its round
     for (uint32_t t = r_start; t < rounds; t++) {
         if (t >= 16) {
             const uint32_t x2 = __shfl_sync(0xffffffffu, win, (t - 2) & 15), x7 = __shfl_sync(0xffffffffu, win, (t - 7) & 15);
